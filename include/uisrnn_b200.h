@@ -1,0 +1,140 @@
+/*
+ * uisrnn_b200.h -- C ABI of libuisrnn_b200.so: the B200 (sm_100a) implementation of UIS-RNN's
+ * predict() hot path (beam search over GRU hypotheses).
+ *
+ * The reference (google/uis-rnn) has NO native / FFI layer: its only boundary
+ * is the Python API.  This header is the seam a maintainer would bind (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference code it replaces.  All paths are
+ * relative to /root/reference.
+ *
+ * Conventions
+ *   - return 0 on success, negative uis_status on failure; message via uis_last_error()
+ *     (thread-local).  Nothing throws across the ABI.
+ *   - a uis_model is bound to one CUDA device; calls on one handle must be serialised by the
+ *     caller; different handles may be used from different threads/processes.
+ *   - caller owns every input/output buffer; the library owns the handle and its workspace.
+ *   - all device work is ordered on the `stream` argument (a cudaStream_t, NULL = default
+ *     stream).  The *_device entry point does not synchronise; the host-buffer entry point
+ *     returns after the labels have landed in the caller's host buffers.
+ */
+#ifndef UISRNN_B200_H_
+#define UISRNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UIS_ABI_VERSION 1
+
+typedef enum uis_status {
+  UIS_OK = 0,
+  UIS_ERR_INVALID = -1,     /* bad argument (shape, NULL, beam_size < 1, ...)                  */
+  UIS_ERR_UNSUPPORTED = -2, /* shape / option the sm_100a kernels are not instantiated for     */
+  UIS_ERR_CUDA = -3,        /* a CUDA runtime call failed; uis_last_error() has the string     */
+  UIS_ERR_OVERFLOW = -4,    /* a hypothesis opened more than `kcap` clusters; retry with more  */
+  UIS_ERR_NOMEM = -5
+} uis_status;
+
+typedef struct uis_model uis_model; /* opaque */
+
+/* Inference options = the reference's inference_args (uisrnn/arguments.py:172-193). */
+typedef struct uis_predict_opts {
+  int32_t beam_size;      /* --beam_size      (arguments.py:175-180), >= 1                     */
+  int32_t look_ahead;     /* --look_ahead     (arguments.py:181-185), >= 1                     */
+  int32_t test_iteration; /* --test_iteration (arguments.py:186-193), >= 1                     */
+  int32_t kcap;           /* max clusters per hypothesis held on device; 0 = default (32)      */
+  int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
+  int32_t reserved[3];
+} uis_predict_opts;
+
+/* Optional per-call debug / parity taps.  Any pointer may be NULL.  All are HOST buffers
+ * the library fills before uis_predict*() returns (it synchronises the stream if any tap is set). */
+typedef struct uis_debug_taps {
+  int32_t trace_utt;       /* utterance index to trace step by step, -1 = none                 */
+  int32_t trace_capacity;  /* rows available in step_winners / step_scores                     */
+  int32_t* step_winners;   /* [trace_capacity][1+look_ahead]: (parent beam, cluster...) rows,
+                              ranked order, all steps concatenated -- what uisrnn.py:551-556
+                              unravels                                                         */
+  float* step_scores;      /* [trace_capacity] neg_likelihood of each new hypothesis           */
+  int64_t* step_offsets;   /* [steps+1] row offsets per beam step                              */
+  float* final_scores;     /* [U][beam_size] final neg_likelihood per hypothesis (+inf pad)    */
+  int32_t* final_k;        /* [U] clusters in the best hypothesis                              */
+  float* best_mean;        /* [kcap][D]  mean_set   of the best hypothesis of `trace_utt`      */
+  float* best_hidden;      /* [kcap][H]  hidden_set of the best hypothesis of `trace_utt`      */
+  int32_t* best_blocks;    /* [kcap]     block_counts of the best hypothesis of `trace_utt`    */
+} uis_debug_taps;
+
+/* Work counters of the last uis_predict*() call on this handle (for bench.py's accounting). */
+typedef struct uis_stats {
+  int64_t utterances;
+  int64_t frames;          /* un-tiled input rows                                              */
+  int64_t beam_steps;      /* sum over utterances of test_iteration * N / look_ahead (ceil)    */
+  int64_t gru_columns;     /* GRU+MLP evaluations actually performed                           */
+  int64_t weight_passes;   /* full passes over (W_hh, W1, W2) streamed by all CTAs             */
+  int64_t candidates;      /* scored (hypothesis, cluster) candidates                          */
+  int64_t kernel_launches; /* CUDA kernels launched by the call                                */
+  int32_t ctas;            /* persistent CTAs used                                             */
+  int32_t max_k;           /* largest cluster count seen in any hypothesis                     */
+} uis_stats;
+
+int uis_version(void);
+const char* uis_last_error(void);
+
+/*
+ * Replaces UISRNN.__init__ / load (uisrnn/uisrnn.py:83-107, 149-170) for the inference path:
+ * takes the CoreRNN parameters (uisrnn.py:35-43, PyTorch state_dict layout, row-major fp32):
+ *   w_ih [3H,D]  w_hh [3H,H]  b_ih [3H]  b_hh [3H]   (gru.*_l0, gate order r,z,n)
+ *   w1 [H,H] b1 [H] (linear_mean1)   w2 [D,H] b2 [D] (linear_mean2)
+ *   h0 [H] (rnn_init_hidden)   sigma2 [D]
+ * Pointers may be host or device memory (copied, never retained).  Precomputes the per-model
+ * constants CoreRNN(zeros, rnn_init_hidden) that uisrnn.py:435-439 recomputes per candidate.
+ * depth must be 1 (UIS_ERR_UNSUPPORTED otherwise).
+ */
+int uis_model_create(uis_model** out, int device, int D, int H, int depth,
+                     const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* h0, const float* sigma2, double transition_bias,
+                     double crp_alpha);
+int uis_model_destroy(uis_model* m);
+
+/* Copies the per-model constants back (host buffers, fp32): mean0 [D], hidden0 [H]. */
+int uis_model_constants(uis_model* m, float* mean0, float* hidden0);
+
+/*
+ * Replaces UISRNN.predict / predict_single / parallel_predict (uisrnn/uisrnn.py:479-623) for a
+ * list of U utterances held in HOST memory:
+ *   seqs[u]      -> row-major float64 [n_frames[u], D]   (the ndarray the reference validates at
+ *                   uisrnn.py:511-521; cast to fp32 on the device, = uisrnn.py:525-526)
+ *   labels_out[u]-> int32 [n_frames[u]]  = beam_set[0].trace[-N:] (uisrnn.py:561)
+ * Host->device copies, the beam search and the device->host copy of the labels all happen
+ * inside the call.  Utterances are independent; they are scheduled longest-first over
+ * persistent CTAs.
+ */
+int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U,
+                const uis_predict_opts* opts, int32_t* const* labels_out,
+                const uis_debug_taps* taps, void* stream);
+
+/*
+ * Same search with inputs already resident in HBM:
+ *   x_dev      fp32 [frame_offsets[U], D] (all utterances concatenated), device memory
+ *   frame_offsets  HOST int64 [U+1]
+ *   labels_dev int32 [frame_offsets[U]], device memory
+ * Asynchronous on `stream` unless taps != NULL.
+ */
+int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_offsets, int U,
+                       const uis_predict_opts* opts, int32_t* labels_dev,
+                       const uis_debug_taps* taps, void* stream);
+
+/* Device bytes uis_predict_device() will hold for this problem (workspace is cached in the handle). */
+size_t uis_predict_workspace_bytes(uis_model* m, const int64_t* frame_offsets, int U,
+                                   const uis_predict_opts* opts);
+
+int uis_get_stats(uis_model* m, uis_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UISRNN_B200_H_ */

@@ -1,0 +1,139 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (ctypes -> libuisrnn_b200.so),
+against (a) golden vectors produced by the unmodified reference and (b) the CPU oracle on fresh
+seeded inputs.  Labels must be identical; scores within 1e-5 relative; GRU hidden states and
+running means within 1e-5 absolute."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, load_weights, oracle_model, rel_err, small_cases, toy_utterances, uis_oracle
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5
+STATE_ATOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def native():
+  from uisrnn_b200 import native as nat
+  nat.load_library()
+  return nat
+
+
+@pytest.fixture(scope='module')
+def small_model(native):
+  return native.NativeModel(load_weights('model_small.npz'))
+
+
+@pytest.fixture(scope='module')
+def toy_model(native):
+  return native.NativeModel(load_weights('model_toy100.npz'))
+
+
+def test_model_constants_match_oracle(small_model, toy_model):
+  for nm, name in ((small_model, 'model_small.npz'), (toy_model, 'model_toy100.npz')):
+    om = oracle_model(name)
+    mean0, hidden0 = nm.constants()
+    assert np.max(np.abs(mean0 - om.mean0)) < STATE_ATOL
+    assert np.max(np.abs(hidden0 - om.hidden0[0])) < STATE_ATOL
+
+
+@pytest.mark.parametrize('case', [c for c in small_cases() if c['look_ahead'] == 1],
+                         ids=lambda c: c['name'])
+def test_small_cases_match_reference_golden(small_model, case):
+  labs, dbg = small_model.predict([case['x']], beam_size=case['beam_size'], look_ahead=1,
+                                  test_iteration=case['test_iteration'], trace_utt=0)
+  assert labs[0].tolist() == case['labels'].tolist()
+  assert np.array_equal(dbg['off'], case['off'])
+  assert np.array_equal(dbg['win'], case['win'])
+  assert rel_err(dbg['score'], case['score']) < SCORE_RTOL
+  nb = len(case['final_scores'])
+  assert rel_err(dbg['final_scores'][0][:nb], case['final_scores']) < SCORE_RTOL
+  assert np.all(np.isinf(dbg['final_scores'][0][nb:]))
+  assert np.max(np.abs(dbg['best_hidden'] - case['final_hidden'][:, 0, :])) < STATE_ATOL
+  assert np.max(np.abs(dbg['best_mean'] - case['final_mean'])) < STATE_ATOL
+  assert np.array_equal(dbg['best_blocks'], case['final_blocks'])
+
+
+def test_toy_testing_data_labels_identical_to_reference(toy_model):
+  """North star: integer-exact labels on all 25 utterances of data/toy_testing_data.npz."""
+  xs, labs = toy_utterances()
+  got = toy_model.predict(xs)
+  for i, (g, want) in enumerate(zip(got, labs)):
+    assert g.tolist() == want.tolist(), 'utterance %d' % i
+  st = toy_model.stats()
+  assert st['frames'] == sum(len(x) for x in xs) and st['beam_steps'] == 2 * st['frames']
+
+
+@pytest.mark.parametrize('idx', [0, 1])
+def test_toy_trace_matches_reference(toy_model, idx):
+  xs, _ = toy_utterances()
+  g = np.load(GOLDEN + '/toy_trace.npz')
+  _, dbg = toy_model.predict([xs[idx]], trace_utt=0)
+  assert np.array_equal(dbg['win'], g['u%d_win' % idx])
+  assert rel_err(dbg['score'], g['u%d_score' % idx]) < SCORE_RTOL
+  assert np.max(np.abs(dbg['best_hidden'] - g['u%d_final_hidden' % idx][:, 0, :])) < STATE_ATOL
+  assert np.max(np.abs(dbg['best_mean'] - g['u%d_final_mean' % idx])) < STATE_ATOL
+
+
+def test_synth500_labels_identical_to_reference(toy_model):
+  """BASELINE config 2 shape (500-frame, 256-d, beam 10): reference labels are golden."""
+  from uisrnn_b200.synth import synth_utt
+  g = np.load(GOLDEN + '/synth500.npz')
+  xs = [synth_utt(int(s))[0] for s in g['seeds']]
+  got = toy_model.predict(xs)
+  for o, want in zip(got, g['labels']):
+    assert o.tolist() == want.tolist()
+
+
+@pytest.mark.parametrize('beam,titer', [(10, 2), (4, 1), (32, 2), (1, 2)])
+def test_fresh_inputs_match_oracle(small_model, beam, titer):
+  from uisrnn_b200.synth import synth_utt
+  om = oracle_model('model_small.npz')
+  xs = [synth_utt(9000 + i, n_frames=n, dim=64, n_spk=k, noise=0.08)[0]
+        for i, (n, k) in enumerate([(70, 3), (1, 1), (33, 2), (120, 4), (2, 2), (64, 3)])]
+  got = small_model.predict(xs, beam_size=beam, test_iteration=titer)
+  for x, o in zip(xs, got):
+    want = uis_oracle.predict_single(om, x, beam_size=beam, look_ahead=1, test_iteration=titer)
+    assert o.tolist() == want
+
+
+def test_ragged_and_empty_batch(small_model):
+  from uisrnn_b200.synth import synth_utt
+  assert small_model.predict([]) == []
+  xs = [np.zeros((0, 64)), synth_utt(1, n_frames=5, dim=64)[0]]
+  got = small_model.predict(xs)
+  assert len(got[0]) == 0 and len(got[1]) == 5
+
+
+def test_many_utterances_are_independent_of_batching(toy_model):
+  """Size-independent property: predict(list) == [predict(x) for x in list], any CTA count."""
+  from uisrnn_b200.synth import synth_utt
+  xs = [synth_utt(3000 + i, n_frames=40 + 7 * (i % 5))[0] for i in range(40)]
+  together = toy_model.predict(xs)
+  few_ctas = toy_model.predict(xs, n_ctas=3)
+  for i in (0, 7, 39):
+    alone = toy_model.predict([xs[i]])[0]
+    assert alone.tolist() == together[i].tolist() == few_ctas[i].tolist()
+  # permutation invariance of the result
+  perm = np.random.default_rng(0).permutation(len(xs))
+  shuffled = toy_model.predict([xs[i] for i in perm])
+  for j, i in enumerate(perm):
+    assert shuffled[j].tolist() == together[i].tolist()
+
+
+def test_kcap_overflow_fails_loudly(small_model, native):
+  from uisrnn_b200.synth import synth_utt
+  x = synth_utt(77, n_frames=60, dim=64, n_spk=4, noise=0.08)[0]
+  with pytest.raises(native.NativeError) as ei:
+    small_model.predict([x], kcap=1)
+  assert ei.value.code == native.UIS_ERR_OVERFLOW
+
+
+def test_unsupported_options_fail_loudly(small_model, native):
+  x = np.zeros((4, 64))
+  with pytest.raises(native.NativeError) as ei:
+    small_model.predict([x], look_ahead=2)
+  assert ei.value.code == native.UIS_ERR_UNSUPPORTED
+  with pytest.raises(native.NativeError):
+    small_model.predict([x], beam_size=0)

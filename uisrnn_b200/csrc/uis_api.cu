@@ -1,0 +1,496 @@
+// C ABI of libuisrnn_b200.so (see include/uisrnn_b200.h).  Host-side orchestration only:
+// weight re-layout at model creation, workspace management, utterance scheduling (longest
+// first), kernel launches.  No PyTorch types, no CPU compute fallback: if the kernels are not
+// instantiated for a shape the call fails with UIS_ERR_UNSUPPORTED.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/uisrnn_b200.h"
+#include "uis_beam.cuh"
+#include "uis_prepass.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(UIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) return fail(UIS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+constexpr int kMP = 12;  // GRU columns per weight pass (see uis_beam.cuh)
+
+}  // namespace
+
+struct uis_model {
+  int device = 0, D = 0, H = 0, num_sms = 0;
+  double p0 = 0, alpha = 0;
+  // weights, k-major
+  DevBuf wih_t, whh_t, w1_t, w2_t, bih, bhh, b1, b2, wvec, mean0, hidden0;
+  // log tables
+  DevBuf logn, logtot;
+  int log_cap = 0;
+  // workspace
+  DevBuf x64, x32, gi, row_off, order, pool_mean, pool_hidden, bp, queue_stats, labels, status;
+  DevBuf dbg_win, dbg_score, dbg_off, dbg_final_scores, dbg_final_k, dbg_best_mean, dbg_best_hidden,
+      dbg_best_blocks;
+  // last call
+  uis_stats stats{};
+  int last_U = 0;
+  cudaStream_t last_stream = nullptr;
+  bool stats_pending = false;
+};
+
+namespace {
+
+template <int H, int D>
+int launch_beam(const uis::BeamParams& p, int ctas, cudaStream_t st) {
+  const uis::SmemLayout L = uis::make_layout<H, D, kMP>(p.B, p.Kcap);
+  if (L.total > 227 * 1024)
+    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d needs %u B of shared memory (> 227 KB); lower kcap",
+                p.B, p.Kcap, L.total);
+  auto kern = uis::uis_beam_kernel<H, D, kMP>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  kern<<<ctas, H + 32, L.total, st>>>(p);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+bool shape_supported(int H, int D) {
+  return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64);
+}
+
+int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t st) {
+  if (H == 512 && D == 256) return launch_beam<512, 256>(p, ctas, st);
+  if (H == 256 && D == 128) return launch_beam<256, 128>(p, ctas, st);
+  if (H == 128 && D == 64) return launch_beam<128, 64>(p, ctas, st);
+  return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+}
+
+int fetch(std::vector<float>& dst, const float* src, size_t n) {
+  dst.resize(n);
+  CU(cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDefault));
+  return 0;
+}
+
+int upload(DevBuf& b, const void* src, size_t bytes) {
+  if (int rc = b.ensure(bytes)) return rc;
+  CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+std::vector<float> transpose(const std::vector<float>& w, int rows, int cols) {
+  std::vector<float> t((size_t)rows * cols);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = w[(size_t)r * cols + c];
+  return t;
+}
+
+int ensure_log_tables(uis_model* m, int max_tn) {
+  const int need = max_tn + 2;
+  if (need <= m->log_cap) return 0;
+  const int cap = std::max(need, 4096);
+  std::vector<double> ln(cap), lt(cap);
+  ln[0] = -INFINITY;
+  for (int i = 1; i < cap; ++i) ln[i] = std::log((double)i);             // np.log(block_counts[c])
+  for (int i = 0; i < cap; ++i) lt[i] = std::log((double)i + m->alpha);  // np.log(sum(block_counts) + alpha)
+  if (int rc = upload(m->logn, ln.data(), cap * sizeof(double))) return rc;
+  if (int rc = upload(m->logtot, lt.data(), cap * sizeof(double))) return rc;
+  m->log_cap = cap;
+  return 0;
+}
+
+struct Plan {
+  int B, L, T, Kcap, ctas, P, maxN;
+  long long rows;
+};
+
+int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o, Plan* pl) {
+  if (!m || !o || (U > 0 && !off)) return fail(UIS_ERR_INVALID, "null argument");
+  if (U < 0) return fail(UIS_ERR_INVALID, "U < 0");
+  if (o->beam_size < 1 || o->look_ahead < 1 || o->test_iteration < 1)
+    return fail(UIS_ERR_INVALID, "beam_size, look_ahead and test_iteration must be >= 1");
+  if (o->look_ahead != 1)
+    return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d: the sm_100a kernel implements look_ahead=1 only", o->look_ahead);
+  if (o->beam_size > 32) return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > 32 not supported", o->beam_size);
+  pl->B = o->beam_size;
+  pl->L = o->look_ahead;
+  pl->T = o->test_iteration;
+  pl->Kcap = o->kcap > 0 ? o->kcap : 32;
+  if (pl->Kcap > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
+  pl->P = pl->B * pl->Kcap + pl->B + 1;
+  pl->rows = U > 0 ? off[U] : 0;
+  int maxN = 0;
+  for (int u = 0; u < U; ++u) {
+    const long long n = off[u + 1] - off[u];
+    if (n < 0) return fail(UIS_ERR_INVALID, "frame_offsets not monotone");
+    if (n * pl->T > (1ll << 30)) return fail(UIS_ERR_INVALID, "utterance too long");
+    maxN = std::max<long long>(maxN, n);
+  }
+  pl->maxN = std::max(maxN, 1);
+  int ctas = o->n_ctas > 0 ? o->n_ctas : m->num_sms;
+  pl->ctas = std::max(1, std::min(ctas, std::max(U, 1)));
+  return 0;
+}
+
+size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
+  size_t b = 0;
+  b += (size_t)pl.rows * 3 * m->H * 4;                                  // gi
+  b += (size_t)pl.ctas * pl.P * (m->D + m->H) * 4;                      // slot pools
+  b += (size_t)pl.ctas * pl.maxN * pl.B * 4;                            // back-pointers
+  b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
+  return b;
+}
+
+int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, const Plan& pl, int32_t* labels_dev,
+               const uis_debug_taps* taps, cudaStream_t st) {
+  const int H = m->H, D = m->D;
+  m->stats = uis_stats{};
+  m->stats.utterances = U;
+  m->stats.frames = pl.rows;
+  m->stats.ctas = pl.ctas;
+  m->last_U = U;
+  m->last_stream = st;
+  m->stats_pending = false;
+  if (U == 0 || pl.rows == 0) {
+    return 0;
+  }
+  long long max_tn = 0;
+  for (int u = 0; u < U; ++u) max_tn = std::max<long long>(max_tn, (off[u + 1] - off[u]) * pl.T);
+  if (int rc = ensure_log_tables(m, (int)max_tn)) return rc;
+
+  // schedule: longest utterance first (LPT) -- steps are strictly sequential per utterance
+  std::vector<int> order(U);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+  std::vector<long long> off_ll(off, off + U + 1);
+
+  if (int rc = m->row_off.ensure((U + 1) * sizeof(long long))) return rc;
+  if (int rc = m->order.ensure(U * sizeof(int))) return rc;
+  if (int rc = m->status.ensure(U * sizeof(int))) return rc;
+  if (int rc = m->queue_stats.ensure(16 * sizeof(unsigned long long))) return rc;
+  if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
+  if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.P * D * sizeof(float))) return rc;
+  if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.P * H * sizeof(float))) return rc;
+  if (int rc = m->bp.ensure((size_t)pl.ctas * pl.maxN * pl.B * sizeof(unsigned))) return rc;
+
+  CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(m->queue_stats.p, 0, 16 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(m->status.p, 0xff, U * sizeof(int), st));
+
+  uis::BeamParams p{};
+  p.whh_t = m->whh_t.as<float>(); p.w1_t = m->w1_t.as<float>(); p.w2_t = m->w2_t.as<float>();
+  p.bhh = m->bhh.as<float>(); p.b1 = m->b1.as<float>(); p.b2 = m->b2.as<float>();
+  p.wvec = m->wvec.as<float>(); p.mean0 = m->mean0.as<float>(); p.hidden0 = m->hidden0.as<float>();
+  p.log_p0 = std::log(m->p0);          // np.log(self.transition_bias)      uisrnn.py:418
+  p.log_1mp0 = std::log(1.0 - m->p0);  // np.log(1 - self.transition_bias)  uisrnn.py:416
+  p.log_alpha = std::log(m->alpha);    // np.log(self.crp_alpha)            uisrnn.py:445
+  p.logn = m->logn.as<double>(); p.logtot = m->logtot.as<double>();
+  p.x = x_dev; p.gi = m->gi.as<float>();
+  p.row_off = m->row_off.as<long long>(); p.order = m->order.as<int>();
+  p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN;
+  p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>();
+  p.bp = m->bp.as<unsigned>();
+  p.queue = m->queue_stats.as<int>();
+  p.stats = m->queue_stats.as<unsigned long long>() + 8;
+  p.labels = labels_dev; p.status = m->status.as<int>();
+  p.trace_utt = -1;
+
+  long long trace_steps = 0;
+  if (taps) {
+    if (taps->final_scores) {
+      if (int rc = m->dbg_final_scores.ensure((size_t)U * pl.B * 4)) return rc;
+      p.dbg_final_scores = m->dbg_final_scores.as<float>();
+      if (int rc = m->dbg_final_k.ensure((size_t)U * 4)) return rc;
+      p.dbg_final_k = m->dbg_final_k.as<int>();
+    }
+    if (taps->trace_utt >= 0 && taps->trace_utt < U) {
+      p.trace_utt = taps->trace_utt;
+      p.trace_capacity = std::max(taps->trace_capacity, 0);
+      trace_steps = (off[p.trace_utt + 1] - off[p.trace_utt]) * pl.T;
+      if (taps->step_winners && p.trace_capacity > 0) {
+        if (int rc = m->dbg_win.ensure((size_t)p.trace_capacity * 8)) return rc;
+        if (int rc = m->dbg_score.ensure((size_t)p.trace_capacity * 4)) return rc;
+        if (int rc = m->dbg_off.ensure((size_t)(trace_steps + 1) * 8)) return rc;
+        p.dbg_win = m->dbg_win.as<int>(); p.dbg_score = m->dbg_score.as<float>();
+        p.dbg_off = m->dbg_off.as<long long>();
+      }
+      if (taps->best_mean) {
+        if (int rc = m->dbg_best_mean.ensure((size_t)pl.Kcap * D * 4)) return rc;
+        if (int rc = m->dbg_best_hidden.ensure((size_t)pl.Kcap * H * 4)) return rc;
+        if (int rc = m->dbg_best_blocks.ensure((size_t)pl.Kcap * 4)) return rc;
+        p.dbg_best_mean = m->dbg_best_mean.as<float>(); p.dbg_best_hidden = m->dbg_best_hidden.as<float>();
+        p.dbg_best_blocks = m->dbg_best_blocks.as<int>();
+      }
+    }
+  }
+
+  // kernel 1: input projection GEMM
+  {
+    dim3 grid((3 * H + uis::PBN - 1) / uis::PBN, (unsigned)((pl.rows + uis::PBM - 1) / uis::PBM));
+    uis::input_proj_kernel<<<grid, 256, 0, st>>>(x_dev, m->wih_t.as<float>(), m->bih.as<float>(), m->gi.as<float>(),
+                                                (int)pl.rows, 3 * H, D);
+    CU(cudaGetLastError());
+  }
+  // kernel 2: persistent beam search
+  if (int rc = dispatch_beam(H, D, p, pl.ctas, st)) return rc;
+  m->stats.kernel_launches = 2;
+  m->stats_pending = true;
+
+  if (taps) {
+    CU(cudaStreamSynchronize(st));
+    if (p.dbg_final_scores) {
+      CU(cudaMemcpy(taps->final_scores, p.dbg_final_scores, (size_t)U * pl.B * 4, cudaMemcpyDeviceToHost));
+      if (taps->final_k) CU(cudaMemcpy(taps->final_k, p.dbg_final_k, (size_t)U * 4, cudaMemcpyDeviceToHost));
+    }
+    if (p.dbg_win) {
+      CU(cudaMemcpy(taps->step_winners, p.dbg_win, (size_t)p.trace_capacity * 8, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(taps->step_scores, p.dbg_score, (size_t)p.trace_capacity * 4, cudaMemcpyDeviceToHost));
+      if (taps->step_offsets)
+        CU(cudaMemcpy(taps->step_offsets, p.dbg_off, (size_t)(trace_steps + 1) * 8, cudaMemcpyDeviceToHost));
+    }
+    if (p.dbg_best_mean) {
+      CU(cudaMemcpy(taps->best_mean, p.dbg_best_mean, (size_t)pl.Kcap * D * 4, cudaMemcpyDeviceToHost));
+      if (taps->best_hidden)
+        CU(cudaMemcpy(taps->best_hidden, p.dbg_best_hidden, (size_t)pl.Kcap * H * 4, cudaMemcpyDeviceToHost));
+      if (taps->best_blocks)
+        CU(cudaMemcpy(taps->best_blocks, p.dbg_best_blocks, (size_t)pl.Kcap * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  return 0;
+}
+
+// Pull the device-side counters and per-utterance status of the last call (synchronises).
+int collect(uis_model* m) {
+  if (!m->stats_pending) return 0;
+  CU(cudaStreamSynchronize(m->last_stream));
+  unsigned long long s[8];
+  CU(cudaMemcpy(s, m->queue_stats.as<unsigned long long>() + 8, sizeof s, cudaMemcpyDeviceToHost));
+  m->stats.gru_columns = (int64_t)s[0];
+  m->stats.weight_passes = (int64_t)s[1];
+  m->stats.candidates = (int64_t)s[2];
+  m->stats.beam_steps = (int64_t)s[3];
+  m->stats.max_k = (int32_t)s[4];
+  m->stats_pending = false;
+  std::vector<int> status(m->last_U);
+  CU(cudaMemcpy(status.data(), m->status.p, (size_t)m->last_U * sizeof(int), cudaMemcpyDeviceToHost));
+  int overflow = 0, bad = 0;
+  for (int v : status) {
+    if (v == -4) ++overflow;
+    else if (v != 0) ++bad;
+  }
+  if (overflow)
+    return fail(UIS_ERR_OVERFLOW, "%d utterance(s) opened more clusters than kcap; retry with a larger kcap", overflow);
+  if (bad) return fail(UIS_ERR_INVALID, "%d utterance(s) ended with no finite hypothesis", bad);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uis_version(void) { return UIS_ABI_VERSION; }
+const char* uis_last_error(void) { return g_err.c_str(); }
+
+int uis_model_create(uis_model** out, int device, int D, int H, int depth, const float* w_ih, const float* w_hh,
+                     const float* b_ih, const float* b_hh, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* h0, const float* sigma2, double transition_bias,
+                     double crp_alpha) {
+  if (!out) return fail(UIS_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!w_ih || !w_hh || !b_ih || !b_hh || !w1 || !b1 || !w2 || !b2 || !h0 || !sigma2)
+    return fail(UIS_ERR_INVALID, "NULL weight pointer");
+  if (depth != 1) return fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the sm_100a kernel implements depth 1 only", depth);
+  if (!shape_supported(H, D))
+    return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  if (!(transition_bias > 0.0 && transition_bias < 1.0))
+    return fail(UIS_ERR_INVALID, "transition_bias must be in (0,1), got %g", transition_bias);
+  if (!(crp_alpha > 0.0)) return fail(UIS_ERR_INVALID, "crp_alpha must be > 0");
+  CU(cudaSetDevice(device));
+  uis_model* m = new uis_model();
+  m->device = device; m->D = D; m->H = H; m->p0 = transition_bias; m->alpha = crp_alpha;
+  int rc = 0;
+  auto body = [&]() -> int {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    std::vector<float> v;
+    if (int r = fetch(v, w_ih, (size_t)3 * H * D)) return r;
+    { auto t = transpose(v, 3 * H, D); if (int r = upload(m->wih_t, t.data(), t.size() * 4)) return r; }
+    if (int r = fetch(v, w_hh, (size_t)3 * H * H)) return r;
+    { auto t = transpose(v, 3 * H, H); if (int r = upload(m->whh_t, t.data(), t.size() * 4)) return r; }
+    if (int r = fetch(v, w1, (size_t)H * H)) return r;
+    { auto t = transpose(v, H, H); if (int r = upload(m->w1_t, t.data(), t.size() * 4)) return r; }
+    if (int r = fetch(v, w2, (size_t)D * H)) return r;
+    { auto t = transpose(v, D, H); if (int r = upload(m->w2_t, t.data(), t.size() * 4)) return r; }
+    if (int r = fetch(v, b_ih, 3 * H)) return r;
+    if (int r = upload(m->bih, v.data(), v.size() * 4)) return r;
+    if (int r = fetch(v, b_hh, 3 * H)) return r;
+    if (int r = upload(m->bhh, v.data(), v.size() * 4)) return r;
+    if (int r = fetch(v, b1, H)) return r;
+    if (int r = upload(m->b1, v.data(), v.size() * 4)) return r;
+    if (int r = fetch(v, b2, D)) return r;
+    if (int r = upload(m->b2, v.data(), v.size() * 4)) return r;
+    if (int r = fetch(v, sigma2, D)) return r;
+    for (float& s : v) s = 1.0f / (2.0f * s);  // weight = 1 / (2 * sigma2), two fp32 ops (uisrnn.py:414)
+    if (int r = upload(m->wvec, v.data(), v.size() * 4)) return r;
+    std::vector<float> h0v;
+    if (int r = fetch(h0v, h0, H)) return r;
+    DevBuf h0d;
+    if (int r = upload(h0d, h0v.data(), H * 4)) return r;
+    if (int r = m->mean0.ensure(D * 4)) return r;
+    if (int r = m->hidden0.ensure(H * 4)) return r;
+    uis::init_state_kernel<<<1, H, 3 * H * sizeof(float)>>>(m->whh_t.as<float>(), m->w1_t.as<float>(),
+                                                           m->w2_t.as<float>(), m->bih.as<float>(),
+                                                           m->bhh.as<float>(), m->b1.as<float>(), m->b2.as<float>(),
+                                                           h0d.as<float>(), H, D, m->mean0.as<float>(),
+                                                           m->hidden0.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    h0d.release();
+    return 0;
+  };
+  rc = body();
+  if (rc) {
+    uis_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return 0;
+}
+
+int uis_model_destroy(uis_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  DevBuf* bufs[] = {&m->wih_t, &m->whh_t, &m->w1_t, &m->w2_t, &m->bih, &m->bhh, &m->b1, &m->b2, &m->wvec, &m->mean0,
+                    &m->hidden0, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
+                    &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
+                    &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
+                    &m->dbg_best_hidden, &m->dbg_best_blocks};
+  for (DevBuf* b : bufs) b->release();
+  delete m;
+  return 0;
+}
+
+int uis_model_constants(uis_model* m, float* mean0, float* hidden0) {
+  if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
+  CU(cudaSetDevice(m->device));
+  if (mean0) CU(cudaMemcpy(mean0, m->mean0.p, m->D * 4, cudaMemcpyDeviceToHost));
+  if (hidden0) CU(cudaMemcpy(hidden0, m->hidden0.p, m->H * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+size_t uis_predict_workspace_bytes(uis_model* m, const int64_t* frame_offsets, int U, const uis_predict_opts* opts) {
+  Plan pl;
+  if (make_plan(m, frame_offsets, U, opts, &pl)) return 0;
+  return workspace_bytes(m, pl, U);
+}
+
+int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_offsets, int U,
+                       const uis_predict_opts* opts, int32_t* labels_dev, const uis_debug_taps* taps, void* stream) {
+  Plan pl;
+  if (int rc = make_plan(m, frame_offsets, U, opts, &pl)) return rc;
+  if (U > 0 && pl.rows > 0 && (!x_dev || !labels_dev)) return fail(UIS_ERR_INVALID, "null device buffer");
+  CU(cudaSetDevice(m->device));
+  return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, static_cast<cudaStream_t>(stream));
+}
+
+int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const uis_predict_opts* opts,
+                int32_t* const* labels_out, const uis_debug_taps* taps, void* stream) {
+  if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
+  if (U < 0 || (U > 0 && (!seqs || !n_frames || !labels_out))) return fail(UIS_ERR_INVALID, "null argument");
+  std::vector<int64_t> off(U + 1, 0);
+  for (int u = 0; u < U; ++u) {
+    if (n_frames[u] < 0) return fail(UIS_ERR_INVALID, "negative length");
+    if (n_frames[u] > 0 && (!seqs[u] || !labels_out[u])) return fail(UIS_ERR_INVALID, "null utterance buffer");
+    off[u + 1] = off[u] + n_frames[u];
+  }
+  Plan pl;
+  if (int rc = make_plan(m, off.data(), U, opts, &pl)) return rc;
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = m->D;
+  const size_t n = (size_t)pl.rows * D;
+  if (n == 0) return 0;
+  if (int rc = m->x64.ensure(n * 8)) return rc;
+  if (int rc = m->x32.ensure(n * 4)) return rc;
+  if (int rc = m->labels.ensure((size_t)pl.rows * 4)) return rc;
+  // host -> device: one async copy per utterance straight from the caller's float64 buffers
+  for (int u = 0; u < U; ++u)
+    if (n_frames[u] > 0)
+      CU(cudaMemcpyAsync(m->x64.as<double>() + (size_t)off[u] * D, seqs[u], (size_t)n_frames[u] * D * 8,
+                         cudaMemcpyHostToDevice, st));
+  {
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, (size_t)m->num_sms * 16);
+    uis::cast_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), n);
+    CU(cudaGetLastError());
+  }
+  if (int rc = run_device(m, m->x32.as<float>(), off.data(), U, pl, m->labels.as<int32_t>(), taps, st)) return rc;
+  m->stats.kernel_launches += 1;
+  for (int u = 0; u < U; ++u)
+    if (n_frames[u] > 0)
+      CU(cudaMemcpyAsync(labels_out[u], m->labels.as<int32_t>() + off[u], (size_t)n_frames[u] * 4,
+                         cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return collect(m);
+}
+
+int uis_get_stats(uis_model* m, uis_stats* out) {
+  if (!m || !out) return fail(UIS_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(m->device));
+  const int rc = collect(m);
+  *out = m->stats;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""ctypes binding of libuisrnn_b200.so (C ABI in include/uisrnn_b200.h).
+
+This is the only place the Python host code touches the native library.  There is no CPU
+fallback here: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libuisrnn_b200.so')
+
+UIS_OK = 0
+UIS_ERR_INVALID = -1
+UIS_ERR_UNSUPPORTED = -2
+UIS_ERR_CUDA = -3
+UIS_ERR_OVERFLOW = -4
+UIS_ERR_NOMEM = -5
+
+
+class NativeError(RuntimeError):
+  def __init__(self, code, message):
+    super().__init__('libuisrnn_b200: {} (code {})'.format(message, code))
+    self.code = code
+
+
+class PredictOpts(C.Structure):
+  _fields_ = [('beam_size', C.c_int32), ('look_ahead', C.c_int32), ('test_iteration', C.c_int32),
+              ('kcap', C.c_int32), ('n_ctas', C.c_int32), ('reserved', C.c_int32 * 3)]
+
+
+class DebugTaps(C.Structure):
+  _fields_ = [('trace_utt', C.c_int32), ('trace_capacity', C.c_int32),
+              ('step_winners', C.POINTER(C.c_int32)), ('step_scores', C.POINTER(C.c_float)),
+              ('step_offsets', C.POINTER(C.c_int64)), ('final_scores', C.POINTER(C.c_float)),
+              ('final_k', C.POINTER(C.c_int32)), ('best_mean', C.POINTER(C.c_float)),
+              ('best_hidden', C.POINTER(C.c_float)), ('best_blocks', C.POINTER(C.c_int32))]
+
+
+class Stats(C.Structure):
+  _fields_ = [('utterances', C.c_int64), ('frames', C.c_int64), ('beam_steps', C.c_int64),
+              ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
+              ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32)]
+
+  def as_dict(self):
+    return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+# Every symbol include/uisrnn_b200.h declares (tests check the .so exports all of them).
+EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destroy',
+           'uis_model_constants', 'uis_predict', 'uis_predict_device',
+           'uis_predict_workspace_bytes', 'uis_get_stats')
+
+_lib = None
+
+
+def load_library():
+  """Loads the shared library (once).  Raises if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise NativeError(UIS_ERR_INVALID,
+                      'native library not built: {} is missing (run `python -c "import '
+                      '__graft_entry__ as g; g.build()"`)'.format(LIB_PATH))
+  lib = C.CDLL(LIB_PATH)
+  fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+  lib.uis_version.restype = C.c_int
+  lib.uis_last_error.restype = C.c_char_p
+  lib.uis_model_create.restype = C.c_int
+  lib.uis_model_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int] + \
+      [C.c_void_p] * 10 + [C.c_double, C.c_double]
+  lib.uis_model_destroy.restype = C.c_int
+  lib.uis_model_destroy.argtypes = [C.c_void_p]
+  lib.uis_model_constants.restype = C.c_int
+  lib.uis_model_constants.argtypes = [C.c_void_p, fp, fp]
+  lib.uis_predict.restype = C.c_int
+  lib.uis_predict.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+                              C.POINTER(PredictOpts), C.POINTER(C.c_void_p),
+                              C.POINTER(DebugTaps), C.c_void_p]
+  lib.uis_predict_device.restype = C.c_int
+  lib.uis_predict_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int,
+                                     C.POINTER(PredictOpts), C.c_void_p, C.POINTER(DebugTaps),
+                                     C.c_void_p]
+  lib.uis_predict_workspace_bytes.restype = C.c_size_t
+  lib.uis_predict_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int,
+                                              C.POINTER(PredictOpts)]
+  lib.uis_get_stats.restype = C.c_int
+  lib.uis_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+  del ip
+  _lib = lib
+  return lib
+
+
+def _check(lib, rc):
+  if rc != 0:
+    raise NativeError(rc, lib.uis_last_error().decode('utf-8', 'replace'))
+
+
+def _f32(a):
+  return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class NativeModel:
+  """Owns a `uis_model*`.  Weights are numpy arrays in PyTorch state_dict layout."""
+
+  def __init__(self, weights, device=0):
+    lib = load_library()
+    self._lib = lib
+    self._h = C.c_void_p()
+    w = weights
+    depth = int(w.get('depth', 1))
+    self.H = int(np.asarray(w['w1']).shape[0])
+    self.D = int(np.asarray(w['w2']).shape[0])
+    self.device = device
+    arrs = [_f32(w['weight_ih_l0']), _f32(w['weight_hh_l0']), _f32(w['bias_ih_l0']),
+            _f32(w['bias_hh_l0']), _f32(w['w1']), _f32(w['b1']), _f32(w['w2']), _f32(w['b2']),
+            _f32(np.asarray(w['h0']).reshape(-1)[:self.H] if depth == 1 else w['h0']),
+            _f32(w['sigma2'])]
+    expect = [(3 * self.H, self.D), (3 * self.H, self.H), (3 * self.H,), (3 * self.H,),
+              (self.H, self.H), (self.H,), (self.D, self.H), (self.D,), None, (self.D,)]
+    for a, e in zip(arrs, expect):
+      if e is not None and tuple(a.shape) != e:
+        raise ValueError('weight shape {} != expected {}'.format(a.shape, e))
+    ptrs = [a.ctypes.data_as(C.c_void_p) for a in arrs]
+    _check(lib, lib.uis_model_create(C.byref(self._h), device, self.D, self.H, depth, *ptrs,
+                                     float(w['transition_bias']), float(w['crp_alpha'])))
+
+  def close(self):
+    if getattr(self, '_h', None) is not None and self._h:
+      self._lib.uis_model_destroy(self._h)
+      self._h = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  def constants(self):
+    mean0 = np.empty(self.D, np.float32)
+    hidden0 = np.empty(self.H, np.float32)
+    fp = C.POINTER(C.c_float)
+    _check(self._lib, self._lib.uis_model_constants(self._h, mean0.ctypes.data_as(fp),
+                                                    hidden0.ctypes.data_as(fp)))
+    return mean0, hidden0
+
+  @staticmethod
+  def _opts(beam_size, look_ahead, test_iteration, kcap, n_ctas):
+    return PredictOpts(int(beam_size), int(look_ahead), int(test_iteration), int(kcap), int(n_ctas))
+
+  def _taps(self, trace_utt, n_utt, lengths, beam_size, look_ahead, test_iteration, kcap):
+    """Allocates host buffers for the debug taps; returns (struct, dict of arrays)."""
+    kcap = kcap or 32
+    steps = int(lengths[trace_utt]) * test_iteration if trace_utt >= 0 else 0
+    cap = max(1, steps * beam_size)
+    bufs = {
+        'win': np.full((cap, 1 + look_ahead), -1, np.int32),
+        'score': np.zeros(cap, np.float32),
+        'off': np.zeros(steps + 1, np.int64),
+        'final_scores': np.zeros((n_utt, beam_size), np.float32),
+        'final_k': np.zeros(n_utt, np.int32),
+        'best_mean': np.zeros((kcap, self.D), np.float32),
+        'best_hidden': np.zeros((kcap, self.H), np.float32),
+        'best_blocks': np.zeros(kcap, np.int32),
+    }
+    fp, ip, lp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    t = DebugTaps(int(trace_utt), int(cap), bufs['win'].ctypes.data_as(ip),
+                  bufs['score'].ctypes.data_as(fp), bufs['off'].ctypes.data_as(lp),
+                  bufs['final_scores'].ctypes.data_as(fp), bufs['final_k'].ctypes.data_as(ip),
+                  bufs['best_mean'].ctypes.data_as(fp), bufs['best_hidden'].ctypes.data_as(fp),
+                  bufs['best_blocks'].ctypes.data_as(ip))
+    return t, bufs
+
+  def predict(self, seqs, beam_size=10, look_ahead=1, test_iteration=2, kcap=0, n_ctas=0,
+              trace_utt=None, stream=0):
+    """seqs: list of C-contiguous float64 [N_u, D] arrays (host).  Returns a list of int32
+    label arrays (and a dict of debug arrays when trace_utt is not None)."""
+    n = len(seqs)
+    keep = [np.ascontiguousarray(s, dtype=np.float64) for s in seqs]
+    for s in keep:
+      if s.ndim != 2 or s.shape[1] != self.D:
+        raise ValueError('utterance shape {} does not match D={}'.format(s.shape, self.D))
+    lengths = (C.c_int64 * max(n, 1))(*[s.shape[0] for s in keep])
+    in_ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in keep])
+    outs = [np.empty(s.shape[0], np.int32) for s in keep]
+    out_ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas)
+    taps, bufs, tp = None, None, None
+    if trace_utt is not None:
+      taps, bufs = self._taps(trace_utt, n, [s.shape[0] for s in keep], beam_size, look_ahead,
+                              test_iteration, kcap)
+      tp = C.byref(taps)
+    rc = self._lib.uis_predict(self._h, in_ptrs, lengths, n, C.byref(opts), out_ptrs, tp,
+                               C.c_void_p(stream))
+    _check(self._lib, rc)
+    if bufs is not None:
+      nrows = int(bufs['off'][-1]) if len(bufs['off']) else 0
+      bufs['win'] = bufs['win'][:nrows]
+      bufs['score'] = bufs['score'][:nrows]
+      k = int(bufs['final_k'][trace_utt]) if trace_utt >= 0 else 0
+      bufs['best_mean'] = bufs['best_mean'][:k]
+      bufs['best_hidden'] = bufs['best_hidden'][:k]
+      bufs['best_blocks'] = bufs['best_blocks'][:k]
+      return outs, bufs
+    return outs
+
+  def predict_device(self, x_ptr, frame_offsets, labels_ptr, beam_size=10, look_ahead=1,
+                     test_iteration=2, kcap=0, n_ctas=0, stream=0):
+    """Device-resident variant: x_ptr -> fp32 [rows, D], labels_ptr -> int32 [rows] (raw
+    device addresses, e.g. torch.Tensor.data_ptr()).  Asynchronous on `stream`."""
+    off = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas)
+    rc = self._lib.uis_predict_device(self._h, C.c_void_p(x_ptr),
+                                      off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1,
+                                      C.byref(opts), C.c_void_p(labels_ptr), None,
+                                      C.c_void_p(stream))
+    _check(self._lib, rc)
+
+  def stats(self):
+    s = Stats()
+    _check(self._lib, self._lib.uis_get_stats(self._h, C.byref(s)))
+    return s.as_dict()
