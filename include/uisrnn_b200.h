@@ -78,6 +78,8 @@ typedef struct uis_stats {
   int64_t kernel_launches; /* CUDA kernels launched by the call                                */
   int32_t ctas;            /* persistent CTAs used                                             */
   int32_t max_k;           /* largest cluster count seen in any hypothesis                     */
+  float prepass_ms;        /* device time of the input-projection GEMM (CUDA events on `stream`) */
+  float beam_ms;           /* device time of the persistent beam-search kernel                 */
 } uis_stats;
 
 int uis_version(void);

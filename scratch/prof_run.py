@@ -1,0 +1,18 @@
+"""Small profiling workload: U utterances x N frames through the C ABI (device-resident leg)."""
+import sys, os, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from uisrnn_b200 import native
+from uisrnn_b200.synth import synth_utt
+U = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+w = dict(np.load('tests/golden/model_toy100.npz'))
+m = native.NativeModel(w)
+xs = np.concatenate([synth_utt(5000 + u, n_frames=N)[0] for u in range(U)]).astype(np.float32)
+x = torch.from_numpy(xs).cuda()
+lab = torch.empty(U * N, dtype=torch.int32, device='cuda')
+off = np.arange(U + 1, dtype=np.int64) * N
+for _ in range(reps):
+    m.predict_device(x.data_ptr(), off, lab.data_ptr())
+    st = m.stats()
+print(st, 'frames/s', U * N / (st['beam_ms'] / 1e3))

@@ -44,3 +44,37 @@ def rel_err(a, b):
   a = np.asarray(a, dtype=np.float64)
   b = np.asarray(b, dtype=np.float64)
   return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def compare_trace(win, score, off, gwin, gscore, goff, rtol=1e-5):
+  """Compares two beam-search traces (per-step ranked winners + scores).
+
+  Ranked score lists must agree within `rtol`; the hypotheses (identified by their full label
+  history) must be the same and in the same order, EXCEPT that hypotheses whose float32 scores
+  are within `rtol` of each other may swap ranks, or swap in/out at the beam cut-off (the
+  reference ranks float32 scores with an unstable sort, uisrnn.py:546-549, so order inside a
+  near-tie is not defined by the reference either).  Returns the number of near-tie swaps."""
+  assert np.array_equal(off, goff), 'different beam sizes per step'
+  assert rel_err(score, gscore) < rtol
+  prev_a, prev_b = [()], [()]
+  swaps = 0
+  for s in range(len(off) - 1):
+    lo, hi = int(off[s]), int(off[s + 1])
+    a = [prev_a[int(win[r, 0])] + (int(win[r, 1]),) for r in range(lo, hi)]
+    b = [prev_b[int(gwin[r, 0])] + (int(gwin[r, 1]),) for r in range(lo, hi)]
+    if a != b:
+      sb = {h: float(v) for h, v in zip(b, gscore[lo:hi])}
+      cutoff = float(gscore[hi - 1])
+      for r, h in enumerate(a):
+        v = float(score[lo + r])
+        tol = rtol * max(1.0, abs(v))
+        if h in sb:
+          assert abs(sb[h] - v) <= tol, 'step %d: same hypothesis, different score' % s
+          if b[r] != h:  # rank moved: must be inside a near-tie
+            assert abs(float(gscore[lo + r]) - sb[h]) <= tol, 'step %d: rank moved across a real gap' % s
+            swaps += 1
+        else:  # only allowed for a tie at the cut-off
+          assert abs(v - cutoff) <= tol, 'step %d: different hypothesis set beyond a cut-off tie' % s
+          swaps += 1
+    prev_a, prev_b = a, b
+  return swaps

@@ -86,6 +86,7 @@ struct uis_model {
   int last_U = 0;
   cudaStream_t last_stream = nullptr;
   bool stats_pending = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prepass, after prepass, after beam kernel
 };
 
 namespace {
@@ -274,6 +275,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
     }
   }
 
+  for (auto& e : m->ev)
+    if (!e) CU(cudaEventCreate(&e));
+  CU(cudaEventRecord(m->ev[0], st));
   // kernel 1: input projection GEMM
   {
     dim3 grid((3 * H + uis::PBN - 1) / uis::PBN, (unsigned)((pl.rows + uis::PBM - 1) / uis::PBM));
@@ -281,8 +285,10 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
                                                 (int)pl.rows, 3 * H, D);
     CU(cudaGetLastError());
   }
+  CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
   if (int rc = dispatch_beam(H, D, p, pl.ctas, st)) return rc;
+  CU(cudaEventRecord(m->ev[2], st));
   m->stats.kernel_launches = 2;
   m->stats_pending = true;
 
@@ -320,6 +326,8 @@ int collect(uis_model* m) {
   m->stats.candidates = (int64_t)s[2];
   m->stats.beam_steps = (int64_t)s[3];
   m->stats.max_k = (int32_t)s[4];
+  CU(cudaEventElapsedTime(&m->stats.prepass_ms, m->ev[0], m->ev[1]));
+  CU(cudaEventElapsedTime(&m->stats.beam_ms, m->ev[1], m->ev[2]));
   m->stats_pending = false;
   std::vector<int> status(m->last_U);
   CU(cudaMemcpy(status.data(), m->status.p, (size_t)m->last_U * sizeof(int), cudaMemcpyDeviceToHost));
@@ -417,6 +425,8 @@ int uis_model_destroy(uis_model* m) {
                     &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
                     &m->dbg_best_hidden, &m->dbg_best_blocks};
   for (DevBuf* b : bufs) b->release();
+  for (auto& e : m->ev)
+    if (e) cudaEventDestroy(e);
   delete m;
   return 0;
 }

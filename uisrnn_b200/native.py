@@ -41,10 +41,12 @@ class DebugTaps(C.Structure):
 class Stats(C.Structure):
   _fields_ = [('utterances', C.c_int64), ('frames', C.c_int64), ('beam_steps', C.c_int64),
               ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
-              ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32)]
+              ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32),
+              ('prepass_ms', C.c_float), ('beam_ms', C.c_float)]
 
   def as_dict(self):
-    return {k: int(getattr(self, k)) for k, _ in self._fields_}
+    return {k: (float(getattr(self, k)) if t is C.c_float else int(getattr(self, k)))
+            for k, t in self._fields_}
 
 
 # Every symbol include/uisrnn_b200.h declares (tests check the .so exports all of them).
