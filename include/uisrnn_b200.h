@@ -47,7 +47,9 @@ typedef struct uis_predict_opts {
   int32_t test_iteration; /* --test_iteration (arguments.py:186-193), >= 1                     */
   int32_t kcap;           /* max clusters per hypothesis held on device; 0 = default (32)      */
   int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
-  int32_t reserved[3];
+  int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
+                             0 = auto (2 when U >= 2 * CTAs, else 1), max 4                    */
+  int32_t reserved[2];
 } uis_predict_opts;
 
 /* Optional per-call debug / parity taps.  Any pointer may be NULL.  All are HOST buffers
@@ -80,6 +82,10 @@ typedef struct uis_stats {
   int32_t max_k;           /* largest cluster count seen in any hypothesis                     */
   float prepass_ms;        /* device time of the input-projection GEMM (CUDA events on `stream`) */
   float beam_ms;           /* device time of the persistent beam-search kernel                 */
+  int32_t lanes;           /* lanes per CTA used                                               */
+  int32_t reserved;
+  int64_t phase_cycles[6]; /* SM cycles summed over CTAs: select(score+rank+re-pack), gather,
+                              GRU pass, W1 pass, W2 pass, advance/back-track                   */
 } uis_stats;
 
 int uis_version(void);

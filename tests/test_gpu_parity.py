@@ -114,6 +114,10 @@ def test_many_utterances_are_independent_of_batching(toy_model):
   xs = [synth_utt(3000 + i, n_frames=40 + 7 * (i % 5))[0] for i in range(40)]
   together = toy_model.predict(xs)
   few_ctas = toy_model.predict(xs, n_ctas=3)
+  for lanes in (1, 2, 3):  # lanes share weight passes only; results must not depend on them
+    got = toy_model.predict(xs, n_ctas=5, lanes=lanes)
+    assert toy_model.stats()["lanes"] == min(lanes, 2)  # SMEM limits lanes to 2 at kcap=32
+    assert all(a.tolist() == b.tolist() for a, b in zip(got, together)), 'lanes=%d' % lanes
   for i in (0, 7, 39):
     alone = toy_model.predict([xs[i]])[0]
     assert alone.tolist() == together[i].tolist() == few_ctas[i].tolist()

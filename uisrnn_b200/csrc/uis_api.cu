@@ -65,7 +65,6 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-constexpr int kMP = 12;  // GRU columns per weight pass (see uis_beam.cuh)
 
 }  // namespace
 
@@ -93,15 +92,22 @@ namespace {
 
 template <int H, int D>
 int launch_beam(const uis::BeamParams& p, int ctas, cudaStream_t st) {
-  const uis::SmemLayout L = uis::make_layout<H, D, kMP>(p.B, p.Kcap);
+  const uis::SmemLayout L = uis::make_layout<H, D>(p.B, p.Kcap, p.G);
   if (L.total > 227 * 1024)
-    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d needs %u B of shared memory (> 227 KB); lower kcap",
-                p.B, p.Kcap, L.total);
-  auto kern = uis::uis_beam_kernel<H, D, kMP>;
+    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d lanes=%d needs %u B of shared memory (> 227 KB); lower kcap",
+                p.B, p.Kcap, p.G, L.total);
+  auto kern = uis::uis_beam_kernel<H, D>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  kern<<<ctas, H + 32, L.total, st>>>(p);
+  kern<<<ctas, uis::Cfg<H, D>::NT + 32, L.total, st>>>(p);
   CU(cudaGetLastError());
   return 0;
+}
+
+unsigned smem_bytes(int H, int D, int B, int Kcap, int G) {
+  if (H == 512 && D == 256) return uis::make_layout<512, 256>(B, Kcap, G).total;
+  if (H == 256 && D == 128) return uis::make_layout<256, 128>(B, Kcap, G).total;
+  if (H == 128 && D == 64) return uis::make_layout<128, 64>(B, Kcap, G).total;
+  return 0xffffffffu;
 }
 
 bool shape_supported(int H, int D) {
@@ -149,7 +155,7 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 }
 
 struct Plan {
-  int B, L, T, Kcap, ctas, P, maxN;
+  int B, L, T, Kcap, ctas, P, maxN, G;
   long long rows;
 };
 
@@ -177,15 +183,20 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   }
   pl->maxN = std::max(maxN, 1);
   int ctas = o->n_ctas > 0 ? o->n_ctas : m->num_sms;
-  pl->ctas = std::max(1, std::min(ctas, std::max(U, 1)));
+  // lanes (utterances advanced together by one CTA, sharing each weight pass): 2 when there is
+  // enough work to keep every CTA's lanes busy, else 1 (latency mode); opts->lanes overrides.
+  int G = o->lanes > 0 ? std::min(o->lanes, (int)uis::kMaxLanes) : ((long long)U >= 2ll * ctas ? 2 : 1);
+  while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
+  pl->G = G;
+  pl->ctas = std::max(1, std::min(ctas, std::max((U + G - 1) / G, 1)));
   return 0;
 }
 
 size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
   size_t b = 0;
   b += (size_t)pl.rows * 3 * m->H * 4;                                  // gi
-  b += (size_t)pl.ctas * pl.P * (m->D + m->H) * 4;                      // slot pools
-  b += (size_t)pl.ctas * pl.maxN * pl.B * 4;                            // back-pointers
+  b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->H) * 4;               // slot pools
+  b += (size_t)pl.ctas * pl.G * pl.maxN * pl.B * 4;                     // back-pointers
   b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
   return b;
 }
@@ -197,6 +208,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   m->stats.utterances = U;
   m->stats.frames = pl.rows;
   m->stats.ctas = pl.ctas;
+  m->stats.lanes = pl.G;
   m->last_U = U;
   m->last_stream = st;
   m->stats_pending = false;
@@ -217,15 +229,15 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (int rc = m->row_off.ensure((U + 1) * sizeof(long long))) return rc;
   if (int rc = m->order.ensure(U * sizeof(int))) return rc;
   if (int rc = m->status.ensure(U * sizeof(int))) return rc;
-  if (int rc = m->queue_stats.ensure(16 * sizeof(unsigned long long))) return rc;
+  if (int rc = m->queue_stats.ensure(32 * sizeof(unsigned long long))) return rc;
   if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
-  if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.P * D * sizeof(float))) return rc;
-  if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.P * H * sizeof(float))) return rc;
-  if (int rc = m->bp.ensure((size_t)pl.ctas * pl.maxN * pl.B * sizeof(unsigned))) return rc;
+  if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.G * pl.P * D * sizeof(float))) return rc;
+  if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * H * sizeof(float))) return rc;
+  if (int rc = m->bp.ensure((size_t)pl.ctas * pl.G * pl.maxN * pl.B * sizeof(unsigned))) return rc;
 
   CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(m->queue_stats.p, 0, 16 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(m->queue_stats.p, 0, 32 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(m->status.p, 0xff, U * sizeof(int), st));
 
   uis::BeamParams p{};
@@ -238,7 +250,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.logn = m->logn.as<double>(); p.logtot = m->logtot.as<double>();
   p.x = x_dev; p.gi = m->gi.as<float>();
   p.row_off = m->row_off.as<long long>(); p.order = m->order.as<int>();
-  p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN;
+  p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN; p.G = pl.G;
   p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>();
   p.bp = m->bp.as<unsigned>();
   p.queue = m->queue_stats.as<int>();
@@ -319,8 +331,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 int collect(uis_model* m) {
   if (!m->stats_pending) return 0;
   CU(cudaStreamSynchronize(m->last_stream));
-  unsigned long long s[8];
+  unsigned long long s[16];
   CU(cudaMemcpy(s, m->queue_stats.as<unsigned long long>() + 8, sizeof s, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 6; ++i) m->stats.phase_cycles[i] = (int64_t)s[8 + i];
   m->stats.gru_columns = (int64_t)s[0];
   m->stats.weight_passes = (int64_t)s[1];
   m->stats.candidates = (int64_t)s[2];

@@ -6,15 +6,19 @@
 // loss_func.weighted_mse_loss (loss_func.py:19-41) -- with BeamState (:55-77) kept on device.
 //
 // Mapping to the hardware
-//   * one persistent CTA per SM; a CTA pulls utterances (longest first) from a global queue and
-//     runs ALL test_iteration*N beam steps of an utterance without returning to the host.
+//   * one persistent CTA per SM.  A CTA runs G "lanes"; each lane pulls utterances (longest
+//     first) from a global queue and runs ALL test_iteration*N beam steps of its utterance
+//     without returning to the host.  Lanes only share the weight stream: one pass over the
+//     weights serves the GRU columns of every lane's current step.
 //   * per step the only heavy work is  h' = GRU(x_t, h_src),  mean = W2 relu(W1 h' + b1) + b2  for
-//     the M <= beam_size DISTINCT source states of the step's winners: three skinny
+//     the DISTINCT source states of the step's winners (M <= beam_size per lane): three skinny
 //     (rows x 512) x (512 x M) products.  The fp32 weights (4.7 MB, L2-resident) are streamed
 //     through a 4-stage shared-memory ring by a producer warp with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx); 512 consumer threads each own one hidden unit
-//     (3 gate rows) and keep 3*M accumulators in registers, so each weight element fetched from
-//     L2 feeds M FMAs and no cross-thread reduction is needed.
+//     (cp.async.bulk + mbarrier complete_tx).  Consumer threads hold a register tile of
+//     R rows x 16 columns (R = 6 for the GRU gates, 4 for the MLP layers with the K dimension
+//     split over thread groups) so that each value fetched from shared memory feeds >= 3 FMAs:
+//     the shared-memory return path (one 32-bit register per lane per cycle per SM) -- not
+//     the FMA pipe -- is what bounds a skinny matvec batch otherwise (profiles/r1_v1_*).
 //   * hypothesis state is a slot pool in global memory (L2): slot = (mean[D], hidden[H]) written
 //     once and never modified; a hypothesis is a table of (slot, block count, visit count) per
 //     cluster held in shared memory.  A child differs from its parent in ONE table entry, so the
@@ -29,12 +33,14 @@
 
 namespace uis {
 
-constexpr int kStages = 4;            // weight ring depth
-constexpr int kStageBytes = 24 * 1024; // bytes per ring stage
-constexpr int kInitSlot = 0;          // pool slot holding (mean0, hidden0)
+constexpr int kStages = 4;              // weight ring depth
+constexpr int kStageBytes = 24 * 1024;  // bytes per ring stage
+constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
+constexpr int kCP = 16;                 // GRU columns per weight pass
+constexpr int kMaxLanes = 4;
 
 struct TabEntry {
-  int slot;    // index into the CTA's slot pool
+  int slot;    // index into the lane's slot pool
   int blocks;  // block_counts[c]        (uisrnn.py:431-432, 451)
   int visits;  // #{trace == c}          (uisrnn.py:425-428)
   int pad;
@@ -59,11 +65,11 @@ struct BeamParams {
   const float* gi;          // [rows][3H]  W_ih x + b_ih
   const long long* row_off; // [U + 1]
   const int* order;         // [U] utterance ids, longest first
-  int U, B, Kcap, T, P, maxN;
-  // per-CTA workspace
-  float* pool_mean;    // [ctas][P][D]
-  float* pool_hidden;  // [ctas][P][H]
-  unsigned* bp;        // [ctas][maxN][B]  (parent << 16) | cluster
+  int U, B, Kcap, T, P, maxN, G;
+  // per-(CTA, lane) workspace
+  float* pool_mean;    // [ctas*G][P][D]
+  float* pool_hidden;  // [ctas*G][P][H]
+  unsigned* bp;        // [ctas*G][maxN][B]  (parent << 16) | cluster
   int* queue;          // [1] next position in `order`
   // outputs
   int* labels;  // [rows]
@@ -82,73 +88,98 @@ struct BeamParams {
   int* dbg_best_blocks;    // [Kcap]
 };
 
+template <int V> struct Pow2Floor { static constexpr int value = (V >= 2) ? 2 * Pow2Floor<V / 2>::value : 1; };
+template <> struct Pow2Floor<1> { static constexpr int value = 1; };
+template <> struct Pow2Floor<0> { static constexpr int value = 1; };
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+template <int H_, int D_>
+struct Cfg {
+  static constexpr int H = H_, D = D_;
+  static constexpr int UPT = (H >= 512) ? 2 : 1;  // hidden units per consumer thread
+  static constexpr int NT = H / UPT;              // consumer threads
+  static constexpr int NW = NT / 32;
+  static constexpr int RG = 3 * UPT;              // GRU pass: rows per thread
+  static constexpr int KG1 = UPT, TG1 = NT / KG1, R1 = H / TG1;             // W1 pass: K-groups, rows/thread
+  static constexpr int R2 = (UPT == 2) ? 4 : 1, KG2 = NT * R2 / D, TG2 = NT / KG2;  // W2 pass
+  static constexpr int KT_HH = Pow2Floor<kStageBytes / (12 * H)>::value;  // k-rows per ring stage
+  static constexpr int KT_1 = cmin(Pow2Floor<kStageBytes / (4 * H)>::value, H);
+  static constexpr int KT_2 = cmin(Pow2Floor<kStageBytes / (4 * D)>::value, H);
+  static constexpr int N_HH = H / KT_HH, N_1 = H / KT_1, N_2 = H / KT_2;
+  static constexpr int TILES_PER_PASS = N_HH + N_1 + N_2;
+  static_assert(H % KT_HH == 0 && H % KT_1 == 0 && H % KT_2 == 0, "tile split");
+  static_assert(KT_1 % KG1 == 0 && KT_2 % KG2 == 0, "K split");
+  static_assert(TG2 * R2 == D && TG1 * R1 == H, "row split");
+  static_assert(KG1 * H <= 2 * H && KG2 * D <= 2 * H, "K-split scratch must fit in XA+XB");
+  static_assert(D % 4 == 0 && NT % 32 == 0 && D <= NT, "shape");
+  static_assert((3 * H / 4) + (D / 4) <= NT * 2, "prefetch mapping");
+};
+
 struct SmemLayout {
-  unsigned ring, xa, xb, xt, gi, wv, tabs, meta, candoff, keys, svals, wins, cols, used, bars,
-      misc, total;
+  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, total;
+  // offsets inside one lane block
+  unsigned l_xt, l_gi, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
-template <int H, int D, int MP>
-__host__ __device__ inline SmemLayout make_layout(int B, int Kcap) {
+// lane scalars (ints) ------------------------------------------------------------------------
+enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRACED, LS_NFINITE, LS_KMAX,
+       LS_NWIN, LS_ERR, LS_M, LS_COLBASE, LS_NE, LS_ROW0_LO, LS_ROW0_HI, LS_DBGROWS_LO, LS_DBGROWS_HI,
+       LS_FRESH, LS_COUNT = 24 };
+// CTA scalars
+enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT };
+
+template <int H, int D>
+__host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   SmemLayout L;
   unsigned o = 0;
-  L.ring = o;    o += kStages * kStageBytes;
-  L.xa = o;      o += H * MP * 4;
-  L.xb = o;      o += H * MP * 4;
-  L.xt = o;      o += 2 * D * 4;
-  L.gi = o;      o += 2 * 3 * H * 4;
-  L.wv = o;      o += D * 4;
-  L.tabs = o;    o += 2u * B * Kcap * 16;
-  L.meta = o;    o += 2u * 4 * B * 4;            // K,last,tot,nl  x2 generations
-  L.candoff = o; o += align_up((B + 1) * 4, 16);
+  L.ring = o;  o += kStages * kStageBytes;
+  L.xa = o;    o += H * kCP * 4;
+  L.xb = o;    o += H * kCP * 4;
+  L.wv = o;    o += D * 4;
+  // ---- one lane block
+  unsigned q = 0;
+  L.l_xt = q;      q += 2 * D * 4;
+  L.l_gi = q;      q += 2 * 3 * H * 4;
+  L.l_tabs = q;    q += 2u * B * Kcap * 16;
+  L.l_meta = q;    q += 2u * 4 * B * 4;  // K,last,tot,nl  x2 generations
+  L.l_candoff = q; q += align_up((B + 1) * 4, 16);
   const unsigned ne = (unsigned)B * (Kcap + 1);
-  L.keys = o;    o += align_up(ne * 8, 16);
-  L.svals = o;   o += align_up(ne * 4, 16);
-  L.wins = o;    o += align_up(3u * B * 4, 16);
-  L.cols = o;    o += align_up(5u * B * 4, 16);  // col, colsrc, colnew, colvis, colblk
+  L.l_keys = q;    q += align_up(ne * 8, 16);
+  L.l_svals = q;   q += align_up(ne * 4, 16);
+  L.l_wins = q;    q += align_up(3u * B * 4, 16);
+  L.l_wcol = q;    q += align_up((unsigned)B * 4, 16);
+  L.l_lcol = q;    q += align_up(2u * B * 4, 16);  // lane-local column -> (source slot, new slot)
   const unsigned pw = ((unsigned)B * Kcap + B + 1 + 31) / 32;
-  L.used = o;    o += align_up(pw * 4, 16);
-  L.bars = o;    o += 2 * kStages * 8;
-  L.misc = o;    o += 64;
+  L.l_used = q;    q += align_up(pw * 4, 16);
+  L.l_ls = q;      q += LS_COUNT * 4;
+  L.lane_stride = align_up(q, 16);
+  L.lanes = o;     o += L.lane_stride * G;
+  L.cols = o;      o += align_up(5u * G * B * 4, 16);  // collane, colsrc, colnew, colvis, colgi
+  L.bars = o;      o += 2 * kStages * 8;
+  L.misc = o;      o += 64;
   L.total = o;
   return L;
 }
 
-// misc[] indices
-enum { MI_PUBLISHED = 0, MI_DONE, MI_UIDX, MI_NFINITE, MI_M, MI_NWIN, MI_ERR, MI_KMAX };
-
-template <int V> struct Pow2Floor { static constexpr int value = (V >= 2) ? 2 * Pow2Floor<V / 2>::value : 1; };
-template <> struct Pow2Floor<1> { static constexpr int value = 1; };
-template <> struct Pow2Floor<0> { static constexpr int value = 1; };
-
-template <int H, int D>
-struct Tiles {
-  static constexpr int KT_HH = Pow2Floor<kStageBytes / (12 * H)>::value;  // k-rows of W_hh^T per stage
-  static constexpr int KT_1 = Pow2Floor<kStageBytes / (4 * H)>::value > H ? H : Pow2Floor<kStageBytes / (4 * H)>::value;
-  static constexpr int KT_2 = Pow2Floor<kStageBytes / (4 * D)>::value > H ? H : Pow2Floor<kStageBytes / (4 * D)>::value;
-  static constexpr int N_HH = H / KT_HH, N_1 = H / KT_1, N_2 = H / KT_2;
-  static constexpr int TILES_PER_PASS = N_HH + N_1 + N_2;
-  static_assert(H % KT_HH == 0 && H % KT_1 == 0 && H % KT_2 == 0, "tile split");
-};
-
 // ------------------------------------------------------------------ producer (one thread)
-template <int H, int D>
+template <class C>
 __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, uint64_t* empty,
                               volatile int* misc) {
-  using TL = Tiles<H, D>;
+  constexpr int H = C::H, D = C::D;
   unsigned it = 0;
   int pass = 0;
   for (;;) {
-    while (*(volatile int*)&misc[MI_PUBLISHED] <= pass) {
-      if (*(volatile int*)&misc[MI_DONE]) return;
+    while (misc[MI_PUBLISHED] <= pass) {
+      if (misc[MI_DONE]) return;
       __nanosleep(64);
     }
     __threadfence_block();
     for (int seg = 0; seg < 3; ++seg) {
       const float* src = seg == 0 ? p.whh_t : (seg == 1 ? p.w1_t : p.w2_t);
-      const int ntiles = seg == 0 ? TL::N_HH : (seg == 1 ? TL::N_1 : TL::N_2);
-      const unsigned bytes = seg == 0 ? TL::KT_HH * 3 * H * 4 : (seg == 1 ? TL::KT_1 * H * 4 : TL::KT_2 * D * 4);
+      const int ntiles = seg == 0 ? C::N_HH : (seg == 1 ? C::N_1 : C::N_2);
+      const unsigned bytes = seg == 0 ? C::KT_HH * 3 * H * 4 : (seg == 1 ? C::KT_1 * H * 4 : C::KT_2 * D * 4);
       for (int t = 0; t < ntiles; ++t, ++it) {
         const unsigned s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -161,11 +192,11 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
   }
 }
 
-// Consume one full weight pass without computing (used when a step has no winner, so that the
-// producer, which was already told about the pass, never blocks on a full ring).
-template <int H, int D>
+// Consume one full weight pass without computing (a step with no winner at all), so that the
+// producer, which was already told about the pass, never blocks on a full ring.
+template <class C>
 __device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsigned& it, int lane) {
-  for (int t = 0; t < Tiles<H, D>::TILES_PER_PASS; ++t, ++it) {
+  for (int t = 0; t < C::TILES_PER_PASS; ++t, ++it) {
     const unsigned s = it % kStages, ph = (it / kStages) & 1;
     mbar_wait(&full[s], ph);
     __syncwarp();
@@ -173,166 +204,186 @@ __device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsi
   }
 }
 
-// ------------------------------------------------------------------ consumer passes
-// Thread j owns hidden unit j.  acc layout: [gate][column].
-template <int H, int D, int MP, int NC>
-__device__ __forceinline__ void gru_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
-                                         unsigned& it, const float* __restrict__ XA, float* __restrict__ XB,
-                                         const float* __restrict__ gi, float bhr, float bhz, float bhn,
-                                         int M, const int* __restrict__ colnew, float* __restrict__ pool_hidden,
-                                         int j, int lane) {
-  using TL = Tiles<H, D>;
-  float ar[4 * NC], az[4 * NC], an[4 * NC];
+// ------------------------------------------------------------------ consumer: one weight matrix
+// acc[i][m] += sum_k Wt[k][tl + TG*i] * X[k][m]   for this thread's R rows and its K-group's
+// share (KT/KG k-rows) of every ring tile.  Wt tiles are [KT][ROWS] floats; X is [H][kCP].
+template <class C, int ROWS, int KT, int KG, int R, int NC>
+__device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
+                                         unsigned& it, const float* __restrict__ X, float (&acc)[R][4 * NC],
+                                         int tid, int lane) {
+  constexpr int TG = C::NT / KG;
+  constexpr int KPG = KT / KG;
+  const int kg = tid / TG, tl = tid % TG;
 #pragma unroll
-  for (int i = 0; i < 4 * NC; ++i) ar[i] = az[i] = an[i] = 0.f;
-  for (int tile = 0; tile < TL::N_HH; ++tile, ++it) {
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int m = 0; m < 4 * NC; ++m) acc[i][m] = 0.f;
+  for (int tile = 0; tile < C::H / KT; ++tile, ++it) {
     const unsigned s = it % kStages, ph = (it / kStages) & 1;
     mbar_wait(&full[s], ph);
-    const float* wt = ring + (size_t)s * (kStageBytes / 4);
-#pragma unroll
-    for (int kk = 0; kk < TL::KT_HH; ++kk) {
-      const float wr = wt[kk * 3 * H + j];
-      const float wz = wt[kk * 3 * H + H + j];
-      const float wn = wt[kk * 3 * H + 2 * H + j];
-      const float4* xp = reinterpret_cast<const float4*>(XA + (size_t)(tile * TL::KT_HH + kk) * MP);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float4 x = xp[c];
-        ar[4 * c + 0] = fmaf(wr, x.x, ar[4 * c + 0]); ar[4 * c + 1] = fmaf(wr, x.y, ar[4 * c + 1]);
-        ar[4 * c + 2] = fmaf(wr, x.z, ar[4 * c + 2]); ar[4 * c + 3] = fmaf(wr, x.w, ar[4 * c + 3]);
-        az[4 * c + 0] = fmaf(wz, x.x, az[4 * c + 0]); az[4 * c + 1] = fmaf(wz, x.y, az[4 * c + 1]);
-        az[4 * c + 2] = fmaf(wz, x.z, az[4 * c + 2]); az[4 * c + 3] = fmaf(wz, x.w, az[4 * c + 3]);
-        an[4 * c + 0] = fmaf(wn, x.x, an[4 * c + 0]); an[4 * c + 1] = fmaf(wn, x.y, an[4 * c + 1]);
-        an[4 * c + 2] = fmaf(wn, x.z, an[4 * c + 2]); an[4 * c + 3] = fmaf(wn, x.w, an[4 * c + 3]);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-  // GRU cell, PyTorch gate order r,z,n (uisrnn.py:39-47):  h' = (h - n) * z + n
-  const float gir = gi[j], giz = gi[H + j], gin = gi[2 * H + j];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * MP)[c];
-    const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
-    float hn[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int m = 4 * c + q;
-      const float r = sigmoid_f32(__fadd_rn(gir, __fadd_rn(ar[m], bhr)));
-      const float z = sigmoid_f32(__fadd_rn(giz, __fadd_rn(az[m], bhz)));
-      const float n = tanhf(__fadd_rn(gin, __fmul_rn(r, __fadd_rn(an[m], bhn))));
-      hn[q] = __fadd_rn(__fmul_rn(__fsub_rn(ho[q], n), z), n);
-      if (m < M) pool_hidden[(size_t)colnew[m] * H + j] = hn[q];
-    }
-    reinterpret_cast<float4*>(XB + (size_t)j * MP)[c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-  }
-}
-
-template <int H, int D, int MP, int NC>
-__device__ __forceinline__ void mlp1_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
-                                          unsigned& it, const float* __restrict__ XB, float* __restrict__ XA,
-                                          float b1j, int j, int lane) {
-  using TL = Tiles<H, D>;
-  float a[4 * NC];
-#pragma unroll
-  for (int i = 0; i < 4 * NC; ++i) a[i] = 0.f;
-  for (int tile = 0; tile < TL::N_1; ++tile, ++it) {
-    const unsigned s = it % kStages, ph = (it / kStages) & 1;
-    mbar_wait(&full[s], ph);
-    const float* wt = ring + (size_t)s * (kStageBytes / 4);
-#pragma unroll 8
-    for (int kk = 0; kk < TL::KT_1; ++kk) {
-      const float w = wt[kk * H + j];
-      const float4* xp = reinterpret_cast<const float4*>(XB + (size_t)(tile * TL::KT_1 + kk) * MP);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float4 x = xp[c];
-        a[4 * c + 0] = fmaf(w, x.x, a[4 * c + 0]); a[4 * c + 1] = fmaf(w, x.y, a[4 * c + 1]);
-        a[4 * c + 2] = fmaf(w, x.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(w, x.w, a[4 * c + 3]);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    float4 v;
-    v.x = fmaxf(__fadd_rn(a[4 * c + 0], b1j), 0.f); v.y = fmaxf(__fadd_rn(a[4 * c + 1], b1j), 0.f);
-    v.z = fmaxf(__fadd_rn(a[4 * c + 2], b1j), 0.f); v.w = fmaxf(__fadd_rn(a[4 * c + 3], b1j), 0.f);
-    reinterpret_cast<float4*>(XA + (size_t)j * MP)[c] = v;
-  }
-}
-
-// W2 pass: D output rows, NT = H threads => G2 = H / D thread groups split each tile's k-rows.
-// Partial sums of groups 1.. go through `scratch` (aliases XB, dead after the W1 pass).
-template <int H, int D, int MP, int NC>
-__device__ __forceinline__ void mlp2_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
-                                          unsigned& it, const float* __restrict__ XA, float* __restrict__ scratch,
-                                          float b2d, int M, const int* __restrict__ colsrc,
-                                          const int* __restrict__ colnew, const int* __restrict__ colvis,
-                                          float* __restrict__ pool_mean, int tid, int lane) {
-  using TL = Tiles<H, D>;
-  constexpr int G2 = H / D;
-  constexpr int KPG = TL::KT_2 / G2;
-  static_assert(H % D == 0 && TL::KT_2 % G2 == 0, "W2 split");
-  const int d = tid % D, g = tid / D;
-  float a[4 * NC];
-#pragma unroll
-  for (int i = 0; i < 4 * NC; ++i) a[i] = 0.f;
-  // old means of the source slots (consumed in the epilogue; issued early to hide L2 latency)
-  float mu_old[4 * NC];
-  if (g == 0) {
-#pragma unroll
-    for (int m = 0; m < 4 * NC; ++m) mu_old[m] = (m < M) ? pool_mean[(size_t)colsrc[m] * D + d] : 0.f;
-  }
-  for (int tile = 0; tile < TL::N_2; ++tile, ++it) {
-    const unsigned s = it % kStages, ph = (it / kStages) & 1;
-    mbar_wait(&full[s], ph);
-    const float* wt = ring + (size_t)s * (kStageBytes / 4);
-#pragma unroll 8
+    const float* wt = ring + (size_t)s * (kStageBytes / 4) + (size_t)(kg * KPG) * ROWS + tl;
+    const float4* xp = reinterpret_cast<const float4*>(X + (size_t)(tile * KT + kg * KPG) * kCP);
+#pragma unroll 4
     for (int kq = 0; kq < KPG; ++kq) {
-      const int kk = g * KPG + kq;
-      const float w = wt[kk * D + d];
-      const float4* xp = reinterpret_cast<const float4*>(XA + (size_t)(tile * TL::KT_2 + kk) * MP);
+      float w[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) w[i] = wt[kq * ROWS + TG * i];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const float4 x = xp[c];
-        a[4 * c + 0] = fmaf(w, x.x, a[4 * c + 0]); a[4 * c + 1] = fmaf(w, x.y, a[4 * c + 1]);
-        a[4 * c + 2] = fmaf(w, x.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(w, x.w, a[4 * c + 3]);
+        const float4 x = xp[kq * (kCP / 4) + c];
+        const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          // packed fp32 FMA (sm_100 FFMA2): two IEEE-RN fmas per instruction, w broadcast
+          const float2 w2 = make_float2(w[i], w[i]);
+          float2 a0 = make_float2(acc[i][4 * c + 0], acc[i][4 * c + 1]);
+          float2 a1 = make_float2(acc[i][4 * c + 2], acc[i][4 * c + 3]);
+          a0 = __ffma2_rn(xlo, w2, a0);
+          a1 = __ffma2_rn(xhi, w2, a1);
+          acc[i][4 * c + 0] = a0.x; acc[i][4 * c + 1] = a0.y;
+          acc[i][4 * c + 2] = a1.x; acc[i][4 * c + 3] = a1.y;
+        }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
-  if (G2 > 1) {
-    if (g > 0) {
+}
+
+// Sum the K-groups' partial results through shared memory.  On return out[q][m] holds the full
+// sum for row tid + NT*q (q < RF).  `scratch` = XA..XB (2*H*kCP floats), dead at this point.
+template <class C, int ROWS, int KG, int R, int RF, int NC>
+__device__ __forceinline__ void ksplit_reduce(float (&acc)[R][4 * NC], float* __restrict__ scratch,
+                                              float (&out)[RF][4 * NC], int tid) {
+  if constexpr (KG == 1) {
+    static_assert(R == RF, "direct mapping");
+#pragma unroll
+    for (int q = 0; q < RF; ++q)
+#pragma unroll
+      for (int m = 0; m < 4 * NC; ++m) out[q][m] = acc[q][m];
+  } else {
+    constexpr int TG = C::NT / KG;
+    const int kg = tid / TG, tl = tid % TG;
+    named_bar_sync(1, C::NT);  // every thread is done reading the pass input
+#pragma unroll
+    for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int c = 0; c < NC; ++c)
-        reinterpret_cast<float4*>(scratch + ((size_t)(g - 1) * D + d) * MP)[c] =
-            make_float4(a[4 * c + 0], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
-    }
-    named_bar_sync(1, H);
-  }
-  if (g == 0) {
+        reinterpret_cast<float4*>(scratch + ((size_t)kg * ROWS + tl + TG * i) * kCP)[c] =
+            make_float4(acc[i][4 * c + 0], acc[i][4 * c + 1], acc[i][4 * c + 2], acc[i][4 * c + 3]);
+    named_bar_sync(1, C::NT);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      float v[4] = {a[4 * c + 0], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]};
-      for (int gg = 1; gg < G2; ++gg) {
-        const float4 o = reinterpret_cast<const float4*>(scratch + ((size_t)(gg - 1) * D + d) * MP)[c];
-        v[0] = __fadd_rn(v[0], o.x); v[1] = __fadd_rn(v[1], o.y);
-        v[2] = __fadd_rn(v[2], o.z); v[3] = __fadd_rn(v[3], o.w);
+    for (int q = 0; q < RF; ++q) {
+      const int row = tid + C::NT * q;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < ROWS) {
+          v = reinterpret_cast<const float4*>(scratch + (size_t)row * kCP)[c];
+#pragma unroll
+          for (int g = 1; g < KG; ++g) {
+            const float4 o = reinterpret_cast<const float4*>(scratch + ((size_t)g * ROWS + row) * kCP)[c];
+            v.x = __fadd_rn(v.x, o.x); v.y = __fadd_rn(v.y, o.y); v.z = __fadd_rn(v.z, o.z); v.w = __fadd_rn(v.w, o.w);
+          }
+        }
+        out[q][4 * c + 0] = v.x; out[q][4 * c + 1] = v.y; out[q][4 * c + 2] = v.z; out[q][4 * c + 3] = v.w;
       }
+    }
+    named_bar_sync(1, C::NT);  // scratch may be overwritten by the caller from here on
+  }
+}
+
+// Per-column context of the current weight pass (shared memory, written in phase P4).
+struct ColCtx {
+  const int* lane;  // [Mtot] lane of the column
+  const int* src;   // source slot
+  const int* dst;   // new slot
+  const int* vis;   // visits of the source entry BEFORE this update
+  const int* gi;    // float offset (from smem base) of the lane's current gi row
+};
+
+// ---- one full weight pass (GRU -> W1 -> W2) for columns [m0, m0 + Mp) -----------------------
+template <class C, int NC>
+__device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
+                                         unsigned& it, float* XA, float* XB, const float* smem_f,
+                                         const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
+                                         float* pool_hidden_cta, const float (&bh)[C::RG], const float (&b1r)[C::UPT],
+                                         float b2r, int tid, int lane, long long* ph, long long& tmark) {
+  constexpr int H = C::H, D = C::D, NT = C::NT, UPT = C::UPT;
+  const size_t lane_pool_h = (size_t)p.P * H, lane_pool_m = (size_t)p.P * D;
+  // ---------------- GRU gates: acc[g*UPT + u][m] = (W_h{r,z,n} h_src)[unit tid + NT*u]
+  {
+    float acc[C::RG][4 * NC];
+    lin_pass<C, 3 * H, C::KT_HH, 1, C::RG, NC>(ring, full, empty, it, XA, acc, tid, lane);
+    // GRU cell, PyTorch gate order r,z,n (uisrnn.py:39-47):  h' = (h - n) * z + n
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = 4 * c + q;
-        if (m < M) {
-          const float mval = __fadd_rn(v[q], b2d);
-          const int n = colvis[m];  // visits BEFORE this one (uisrnn.py:425-429)
+    for (int u = 0; u < UPT; ++u) {
+      const int j = tid + NT * u;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * kCP)[c];
+        const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
+        float hn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = 4 * c + q;
+          hn[q] = 0.f;
+          if (m < Mp) {
+            const float* gi = smem_f + cc.gi[m0 + m];
+            const float r = sigmoid_f32(__fadd_rn(gi[j], __fadd_rn(acc[0 * UPT + u][m], bh[0 * UPT + u])));
+            const float z = sigmoid_f32(__fadd_rn(gi[H + j], __fadd_rn(acc[1 * UPT + u][m], bh[1 * UPT + u])));
+            const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(r, __fadd_rn(acc[2 * UPT + u][m], bh[2 * UPT + u]))));
+            hn[q] = __fadd_rn(__fmul_rn(__fsub_rn(ho[q], n), z), n);
+            pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H + j] = hn[q];
+          }
+        }
+        reinterpret_cast<float4*>(XB + (size_t)j * kCP)[c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      }
+    }
+  }
+  named_bar_sync(1, NT);
+  if (tid == 0) { const long long now_ = clock64(); ph[2] += now_ - tmark; tmark = now_; }
+  // ---------------- a = relu(W1 h' + b1)
+  {
+    float acc[C::R1][4 * NC];
+    lin_pass<C, H, C::KT_1, C::KG1, C::R1, NC>(ring, full, empty, it, XB, acc, tid, lane);
+    float out[UPT][4 * NC];
+    ksplit_reduce<C, H, C::KG1, C::R1, UPT, NC>(acc, XA, out, tid);
+#pragma unroll
+    for (int u = 0; u < UPT; ++u)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float4 v;
+        v.x = fmaxf(__fadd_rn(out[u][4 * c + 0], b1r[u]), 0.f); v.y = fmaxf(__fadd_rn(out[u][4 * c + 1], b1r[u]), 0.f);
+        v.z = fmaxf(__fadd_rn(out[u][4 * c + 2], b1r[u]), 0.f); v.w = fmaxf(__fadd_rn(out[u][4 * c + 3], b1r[u]), 0.f);
+        reinterpret_cast<float4*>(XA + (size_t)(tid + NT * u) * kCP)[c] = v;
+      }
+  }
+  named_bar_sync(1, NT);
+  if (tid == 0) { const long long now_ = clock64(); ph[3] += now_ - tmark; tmark = now_; }
+  // ---------------- mean = W2 a + b2, then the running-mean update of the cluster
+  {
+    // old means of the source slots (issued before the pass to hide the L2 latency)
+    float mu_old[4 * NC];
+#pragma unroll
+    for (int m = 0; m < 4 * NC; ++m)
+      mu_old[m] = (m < Mp && tid < D)
+                      ? pool_mean_cta[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.src[m0 + m] * D + tid]
+                      : 0.f;
+    float acc[C::R2][4 * NC];
+    lin_pass<C, D, C::KT_2, C::KG2, C::R2, NC>(ring, full, empty, it, XA, acc, tid, lane);
+    float out[1][4 * NC];
+    ksplit_reduce<C, D, C::KG2, C::R2, 1, NC>(acc, XA, out, tid);
+    if (tid < D) {
+#pragma unroll
+      for (int m = 0; m < 4 * NC; ++m) {
+        if (m < Mp) {
+          const float mval = __fadd_rn(out[0][m], b2r);
+          const int n = cc.vis[m0 + m];  // visits BEFORE this one (uisrnn.py:425-429)
           // mean_set[c] = (mean_set[c] * (n - 1) + mean) / n   -- fp32, true division
           const float mu = (n == 0) ? mval
                                     : __fdiv_rn(__fadd_rn(__fmul_rn(mu_old[m], (float)(n - 1)), mval), (float)n);
-          pool_mean[(size_t)colnew[m] * D + d] = mu;
+          pool_mean_cta[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.dst[m0 + m] * D + tid] = mu;
         }
       }
     }
@@ -340,34 +391,24 @@ __device__ __forceinline__ void mlp2_pass(const float* __restrict__ ring, uint64
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int H, int D, int MP>
-__global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p) {
-  constexpr int NT = H;        // consumer threads
-  constexpr int NW = NT / 32;  // consumer warps
-  static_assert(D % 4 == 0 && H % 32 == 0 && (3 * H / 4) + (D / 4) <= NT, "shape");
-  static_assert(MP % 4 == 0 && MP <= 12, "MP");
+template <int H, int D>
+__global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const BeamParams p) {
+  using C = Cfg<H, D>;
+  constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   extern __shared__ __align__(128) unsigned char smem[];
-  const SmemLayout L = make_layout<H, D, MP>(p.B, p.Kcap);
+  const int B = p.B, Kcap = p.Kcap, G = p.G;
+  const SmemLayout L = make_layout<H, D>(B, Kcap, G);
+  float* smem_f = reinterpret_cast<float*>(smem);
   float* ring = reinterpret_cast<float*>(smem + L.ring);
   float* XA = reinterpret_cast<float*>(smem + L.xa);
   float* XB = reinterpret_cast<float*>(smem + L.xb);
-  float* xt = reinterpret_cast<float*>(smem + L.xt);
-  float* gis = reinterpret_cast<float*>(smem + L.gi);
   float* wv = reinterpret_cast<float*>(smem + L.wv);
-  TabEntry* tabs = reinterpret_cast<TabEntry*>(smem + L.tabs);
-  int* meta = reinterpret_cast<int*>(smem + L.meta);
-  int* candoff = reinterpret_cast<int*>(smem + L.candoff);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
-  float* svals = reinterpret_cast<float*>(smem + L.svals);
-  int* wins = reinterpret_cast<int*>(smem + L.wins);
-  int* cols = reinterpret_cast<int*>(smem + L.cols);
-  unsigned* used = reinterpret_cast<unsigned*>(smem + L.used);
+  int* colarr = reinterpret_cast<int*>(smem + L.cols);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + kStages;
   volatile int* misc = reinterpret_cast<volatile int*>(smem + L.misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int B = p.B, Kcap = p.Kcap;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -380,105 +421,156 @@ __global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p)
   __syncthreads();
 
   if (warp == NW) {  // ---------------- producer warp
-    if (lane == 0) producer_loop<H, D>(p, ring, full, empty, misc);
+    if (lane == 0) producer_loop<C>(p, ring, full, empty, misc);
     return;
   }
 
   // ---------------- consumer threads (tid < NT); they synchronise on named barrier 1
-  float* pool_mean = p.pool_mean + (size_t)blockIdx.x * p.P * D;
-  float* pool_hidden = p.pool_hidden + (size_t)blockIdx.x * p.P * H;
-  unsigned* bp = p.bp + (size_t)blockIdx.x * p.maxN * B;
-  const int j = tid;
-  const float bhr = p.bhh[j], bhz = p.bhh[H + j], bhn = p.bhh[2 * H + j];
-  const float b1j = p.b1[j];
-  const float b2d = p.b2[tid % D];
-  if (tid < D) {
-    wv[tid] = p.wvec[tid];
-    pool_mean[(size_t)kInitSlot * D + tid] = p.mean0[tid];
-  }
-  pool_hidden[(size_t)kInitSlot * H + j] = p.hidden0[j];
+  auto lane_base = [&](int g) -> unsigned char* { return smem + L.lanes + (size_t)g * L.lane_stride; };
+  auto LSp = [&](int g) -> volatile int* { return reinterpret_cast<volatile int*>(lane_base(g) + L.l_ls); };
+  const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * H;
+  float* pool_mean_cta = p.pool_mean + (size_t)blockIdx.x * G * pool_m_stride;
+  float* pool_hidden_cta = p.pool_hidden + (size_t)blockIdx.x * G * pool_h_stride;
+  unsigned* bp_cta = p.bp + (size_t)blockIdx.x * G * p.maxN * B;
   const unsigned PW = (unsigned)(p.P + 31) / 32;
+  const float INF = __int_as_float(0x7f800000);
+
+  float bh[C::RG], b1r[UPT];
+#pragma unroll
+  for (int i = 0; i < C::RG; ++i) bh[i] = p.bhh[(i / UPT) * H + tid + NT * (i % UPT)];
+#pragma unroll
+  for (int u = 0; u < UPT; ++u) b1r[u] = p.b1[tid + NT * u];
+  const float b2r = (tid < D) ? p.b2[tid] : 0.f;
+  if (tid < D) wv[tid] = p.wvec[tid];
+  for (int g = 0; g < G; ++g) {
+    if (tid < D) pool_mean_cta[g * pool_m_stride + (size_t)kInitSlot * D + tid] = p.mean0[tid];
+    for (int u = 0; u < UPT; ++u)
+      pool_hidden_cta[g * pool_h_stride + (size_t)kInitSlot * H + tid + NT * u] = p.hidden0[tid + NT * u];
+  }
+
+  int* collane = colarr; int* colsrc = colarr + G * B; int* colnew = colarr + 2 * G * B;
+  int* colvis = colarr + 3 * G * B; int* colgi = colarr + 4 * G * B;
+  const ColCtx cc{collane, colsrc, colnew, colvis, colgi};
 
   unsigned it = 0;  // weight-ring tile counter (identical in every consumer thread)
   unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;
   int st_maxk = 0;
+  // per-phase cycle counters (thread 0 only): select, gather, gru, w1, w2, advance
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long tmark = clock64();
+#define UIS_PHASE(i)                         \
+  do {                                       \
+    if (tid == 0) {                          \
+      const long long now_ = clock64();      \
+      ph[i] += now_ - tmark;                 \
+      tmark = now_;                          \
+    }                                        \
+  } while (0)
+
+  // Pull the next non-empty utterance for lane g (one thread).
+  auto lane_fetch = [&](int g) {
+    volatile int* ls = LSp(g);
+    for (;;) {
+      const int uidx = atomicAdd(p.queue, 1);
+      if (uidx >= p.U) { ls[LS_ACTIVE] = 0; ls[LS_FRESH] = 0; return; }
+      const int u = p.order[uidx];
+      const long long row0 = p.row_off[u];
+      const int N = (int)(p.row_off[u + 1] - row0);
+      if (N == 0) {
+        p.status[u] = 0;
+        if (p.dbg_final_scores) {
+          for (int b = 0; b < B; ++b) p.dbg_final_scores[(size_t)u * B + b] = INF;
+          if (p.dbg_final_k) p.dbg_final_k[u] = 0;
+        }
+        continue;
+      }
+      ls[LS_U] = u; ls[LS_N] = N; ls[LS_TN] = p.T * N; ls[LS_T] = 0; ls[LS_NB] = 1; ls[LS_GEN] = 0;
+      ls[LS_ACTIVE] = 1; ls[LS_FAILED] = 0; ls[LS_TRACED] = (u == p.trace_utt); ls[LS_ERR] = 0;
+      ls[LS_ROW0_LO] = (int)(row0 & 0xffffffffll); ls[LS_ROW0_HI] = (int)(row0 >> 32);
+      ls[LS_DBGROWS_LO] = 0; ls[LS_DBGROWS_HI] = 0; ls[LS_FRESH] = 1;
+      int* meta = reinterpret_cast<int*>(lane_base(g) + L.l_meta);  // [gen][field][B]: K,last,tot,nl
+      meta[0] = 0; meta[B] = -1; meta[2 * B] = 0; reinterpret_cast<float*>(meta)[3 * B] = 0.f;
+      if (u == p.trace_utt && p.dbg_off) p.dbg_off[0] = 0;
+      return;
+    }
+  };
+  // All consumer threads: start the cp.async of frame `t` of lane g into buffer (t & 1).
+  auto lane_prefetch = [&](int g, int t) {
+    volatile int* ls = LSp(g);
+    const long long row0 = ((long long)ls[LS_ROW0_HI] << 32) | (unsigned)ls[LS_ROW0_LO];
+    const long long r = row0 + (t % ls[LS_N]);
+    float* gis = reinterpret_cast<float*>(lane_base(g) + L.l_gi) + (t & 1) * 3 * H;
+    float* xts = reinterpret_cast<float*>(lane_base(g) + L.l_xt) + (t & 1) * D;
+    for (int q = tid; q < 3 * H / 4 + D / 4; q += NT) {
+      if (q < 3 * H / 4) cp_async16(gis + q * 4, p.gi + (size_t)r * 3 * H + q * 4);
+      else cp_async16(xts + (q - 3 * H / 4) * 4, p.x + (size_t)r * D + (q - 3 * H / 4) * 4);
+    }
+  };
+
+  if (tid < G) lane_fetch(tid);
+  named_bar_sync(1, NT);
+  for (int g = 0; g < G; ++g)
+    if (LSp(g)[LS_ACTIVE]) lane_prefetch(g, 0);
+  cp_async_commit();
 
   for (;;) {
-    if (tid == 0) misc[MI_UIDX] = atomicAdd(p.queue, 1);
-    named_bar_sync(1, NT);
-    const int uidx = misc[MI_UIDX];
-    if (uidx >= p.U) break;
-    const int u = p.order[uidx];
-    const long long row0 = p.row_off[u];
-    const int N = (int)(p.row_off[u + 1] - row0);
-    const int TN = p.T * N;
-    const bool traced = (u == p.trace_utt);
-    long long dbg_rows = 0;
+    int nact = 0;
+    for (int g = 0; g < G; ++g) nact += LSp(g)[LS_ACTIVE];
+    if (nact == 0) break;
 
-    // generation 0 = one empty hypothesis (uisrnn.py:528)
-    int gen = 0;
+    // ---- P0: publish this step's weight pass; per-lane candidate offsets; land x_t / gi_t
     if (tid == 0) {
-      int* K = meta;  // meta layout: [gen][field][B], fields K,last,tot,nl
-      K[0] = 0; K[B + 0] = -1; K[2 * B + 0] = 0; reinterpret_cast<float*>(K)[3 * B + 0] = 0.f;
-      misc[MI_ERR] = 0;
-      if (traced && p.dbg_off) p.dbg_off[0] = 0;
+      __threadfence_block();
+      misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + 1;
     }
-    int nb = 1;
-    // prefetch the first frame (x row and its input projection) into buffer 0
-    if (N > 0) {
-      if (tid < 3 * H / 4) cp_async16(gis + tid * 4, p.gi + (size_t)row0 * 3 * H + tid * 4);
-      else if (tid < 3 * H / 4 + D / 4) cp_async16(xt + (tid - 3 * H / 4) * 4, p.x + (size_t)row0 * D + (tid - 3 * H / 4) * 4);
-      cp_async_commit();
-    }
-    named_bar_sync(1, NT);
-    bool failed = false;
-
-    for (int t = 0; t < TN; ++t) {
-      int* mK = meta + gen * 4 * B;       // current generation
-      int* mLast = mK + B;
-      int* mTot = mK + 2 * B;
-      float* mNl = reinterpret_cast<float*>(mK + 3 * B);
-      int* nK = meta + (gen ^ 1) * 4 * B;  // next generation
-      int* nLast = nK + B;
-      int* nTot = nK + 2 * B;
-      float* nNl = reinterpret_cast<float*>(nK + 3 * B);
-      const TabEntry* tab = tabs + (size_t)gen * B * Kcap;
-      TabEntry* ntab = tabs + (size_t)(gen ^ 1) * B * Kcap;
-      const int buf = t & 1;
-      const float* xs = xt + buf * D;
-      const float* gs = gis + buf * 3 * H;
-
-      // ---- P0: publish this step's weight pass to the producer; land x_t / gi_t
-      if (tid == 0) {
-        __threadfence_block();
-        misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + 1;
+    if (tid < G) {
+      const int g = tid;
+      volatile int* ls = LSp(g);
+      ls[LS_M] = 0; ls[LS_NWIN] = 0; ls[LS_NE] = 0;
+      if (ls[LS_ACTIVE]) {
+        const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + ls[LS_GEN] * 4 * B;
+        int* candoff = reinterpret_cast<int*>(lane_base(g) + L.l_candoff);
         int off = 0, kmax = 0;
+        const int nb = ls[LS_NB];
         for (int b = 0; b < nb; ++b) { candoff[b] = off; off += mK[b] + 1; kmax = max(kmax, mK[b]); }
         candoff[nb] = off;
-        misc[MI_NFINITE] = 0;
-        misc[MI_KMAX] = kmax;
+        ls[LS_NFINITE] = 0; ls[LS_KMAX] = kmax; ls[LS_NE] = off;
       }
+    }
+    for (int g = 0; g < G; ++g) {
+      unsigned* used = reinterpret_cast<unsigned*>(lane_base(g) + L.l_used);
       for (unsigned w = tid; w < PW; w += NT) used[w] = (w == 0) ? 1u : 0u;  // slot 0 = INIT, always live
-      cp_async_wait_all();
-      named_bar_sync(1, NT);
-      if (t + 1 < TN) {  // prefetch next frame into the other buffer
-        const long long r = row0 + ((t + 1) % N);
-        if (tid < 3 * H / 4) cp_async16(gis + (buf ^ 1) * 3 * H + tid * 4, p.gi + (size_t)r * 3 * H + tid * 4);
-        else if (tid < 3 * H / 4 + D / 4)
-          cp_async16(xt + (buf ^ 1) * D + (tid - 3 * H / 4) * 4, p.x + (size_t)r * D + (tid - 3 * H / 4) * 4);
-        cp_async_commit();
-      }
+    }
+    cp_async_wait_all();
+    named_bar_sync(1, NT);
+    for (int g = 0; g < G; ++g) {  // prefetch the next frame of every running lane
+      volatile int* ls = LSp(g);
+      if (ls[LS_ACTIVE] && ls[LS_T] + 1 < ls[LS_TN]) lane_prefetch(g, ls[LS_T] + 1);
+    }
+    cp_async_commit();
 
-      // ---- P1: score every candidate (b, c <= K_b): one warp each (uisrnn.py:409-420, 434-446)
-      const int NE = candoff[nb];
-      const int kmax = misc[MI_KMAX];
-      for (int e = warp; e < NE; e += NW) {
+    // ---- P1: score every candidate (b, c <= K_b) of every lane: one warp each
+    //          (uisrnn.py:409-420 existing cluster, :434-446 new cluster)
+    {
+      int ne_g[kMaxLanes], ne_tot = 0;
+      for (int g = 0; g < G; ++g) { ne_g[g] = LSp(g)[LS_NE]; ne_tot += ne_g[g]; }
+      for (int f = warp; f < ne_tot; f += NW) {
+        int g = 0, e = f;
+        while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
+        volatile int* ls = LSp(g);
+        const int gen = ls[LS_GEN];
+        const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + gen * 4 * B;
+        const int* mLast = mK + B; const int* mTot = mK + 2 * B;
+        const float* mNl = reinterpret_cast<const float*>(mK + 3 * B);
+        const int* candoff = reinterpret_cast<const int*>(lane_base(g) + L.l_candoff);
+        const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
         int b = 0;
         while (candoff[b + 1] <= e) ++b;
         const int c = e - candoff[b];
         const int Kb = mK[b];
         const TabEntry en = (c < Kb) ? tab[(size_t)b * Kcap + c] : TabEntry{kInitSlot, 0, 0, 0};
-        const float* mu = pool_mean + (size_t)en.slot * D;
+        const float* mu = pool_mean_cta + g * pool_m_stride + (size_t)en.slot * D;
+        const float* xs = reinterpret_cast<const float*>(lane_base(g) + L.l_xt) + (ls[LS_T] & 1) * D;
         // weighted_mse_loss for one row (loss_func.py:33-41): sum_d fl(fl(diff^2) * w_d)
         float acc = 0.f, d0sq = 1.f;
         for (int d = lane * 4; d < D; d += 128) {
@@ -496,46 +588,62 @@ __global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p)
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-          if (c < Kb) atomicOr(&used[en.slot >> 5], 1u << (en.slot & 31));
+          if (c < Kb) atomicOr(reinterpret_cast<unsigned*>(lane_base(g) + L.l_used) + (en.slot >> 5), 1u << (en.slot & 31));
           float mse = acc;
           if (d0sq == 0.f) mse = __fdiv_rn(acc, 0.f);  // zero "non-zero rows" (loss_func.py:36)
           double pen;
-          if (c < Kb) {
-            pen = (c == mLast[b]) ? p.log_1mp0 : (p.log_p0 + p.logn[en.blocks]) - p.logtot[mTot[b]];
-          } else {
-            pen = (p.log_p0 + p.log_alpha) - p.logtot[mTot[b]];
-          }
+          if (c < Kb) pen = (c == mLast[b]) ? p.log_1mp0 : (p.log_p0 + p.logn[en.blocks]) - p.logtot[mTot[b]];
+          else pen = (p.log_p0 + p.log_alpha) - p.logtot[mTot[b]];
           const float loss = __double2float_rn((double)mse - pen);
           const float S = __fadd_rn(mNl[b], loss);
-          svals[e] = S;
-          const unsigned flat = (unsigned)(b * (kmax + 1) + c);
-          keys[e] = ((unsigned long long)float_order_key(S) << 32) | flat;
-          if (S < __int_as_float(0x7f800000)) atomicAdd((int*)&misc[MI_NFINITE], 1);
+          reinterpret_cast<float*>(lane_base(g) + L.l_svals)[e] = S;
+          const unsigned flat = (unsigned)(b * (ls[LS_KMAX] + 1) + c);
+          reinterpret_cast<unsigned long long*>(lane_base(g) + L.l_keys)[e] =
+              ((unsigned long long)float_order_key(S) << 32) | flat;
+          if (S < INF) atomicAdd((int*)&ls[LS_NFINITE], 1);
         }
       }
       named_bar_sync(1, NT);
 
       // ---- P2: rank by counting; the best min(#finite, B) become the new hypotheses (:546-552)
-      const int nwin = min((int)misc[MI_NFINITE], B);
-      for (int e = tid; e < NE; e += NT) {
+      for (int f = tid; f < ne_tot; f += NT) {
+        int g = 0, e = f;
+        while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
+        volatile int* ls = LSp(g);
+        const int nwin = min((int)ls[LS_NFINITE], B);
+        const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(lane_base(g) + L.l_keys);
         const unsigned long long k = keys[e];
         int rank = 0;
-        for (int q = 0; q < NE; ++q) rank += (keys[q] < k) ? 1 : 0;
+        for (int q = 0; q < ne_g[g]; ++q) rank += (keys[q] < k) ? 1 : 0;
         if (rank < nwin) {
+          const int* candoff = reinterpret_cast<const int*>(lane_base(g) + L.l_candoff);
           int b = 0;
           while (candoff[b + 1] <= e) ++b;
+          int* wins = reinterpret_cast<int*>(lane_base(g) + L.l_wins);
           wins[rank] = b;
           wins[B + rank] = e - candoff[b];
-          reinterpret_cast<float*>(wins)[2 * B + rank] = svals[e];
+          reinterpret_cast<float*>(wins)[2 * B + rank] = reinterpret_cast<const float*>(lane_base(g) + L.l_svals)[e];
         }
+        if (e == 0) ls[LS_NWIN] = nwin;
       }
       named_bar_sync(1, NT);
+    }
 
-      // ---- P3: warp 0 assigns GRU columns (distinct source slots) and allocates new slots;
-      //          the other warps copy the parents' tables
-      int* col = cols; int* colsrc = cols + B; int* colnew = cols + 2 * B; int* colvis = cols + 3 * B;
-      if (warp == 0) {
-        // (beam_size <= 32 is enforced by the host)
+    // ---- P3: warp g assigns lane g's GRU columns (distinct source slots) and allocates new
+    //          slots; the remaining warps copy the parents' tables into the next generation
+    if (warp < G) {
+      const int g = warp;
+      volatile int* ls = LSp(g);
+      const int nwin = ls[LS_NWIN];
+      if (ls[LS_ACTIVE] && nwin > 0) {  // (beam_size <= 32 is enforced by the host)
+        const int gen = ls[LS_GEN];
+        const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + gen * 4 * B;
+        const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
+        const int* wins = reinterpret_cast<const int*>(lane_base(g) + L.l_wins);
+        int* wcol = reinterpret_cast<int*>(lane_base(g) + L.l_wcol);
+        int* lcolsrc = reinterpret_cast<int*>(lane_base(g) + L.l_lcol);
+        int* lcolnew = lcolsrc + B;
+        const unsigned* used = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_used);
         const int r = lane;
         int src = -1;
         if (r < nwin) {
@@ -552,8 +660,8 @@ __global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p)
         const int mycol = __popc(fm & ((1u << lane) - 1));
         const int M = __popc(fm);
         const int c_of_first = __shfl_sync(0xffffffffu, mycol, first);
-        if (r < nwin) col[r] = c_of_first;
-        if (isfirst) colsrc[mycol] = src;
+        if (r < nwin) wcol[r] = c_of_first;
+        if (isfirst) lcolsrc[mycol] = src;
         // allocate M free slots from the bitmap (any free slot will do)
         int cnt = 0;
         for (unsigned w = lane; w < PW; w += 32) {
@@ -574,136 +682,218 @@ __global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p)
           while (fr && idx < M) {
             const int bit = __ffs(fr) - 1;
             fr &= fr - 1;
-            colnew[idx++] = (int)(w * 32 + bit);
+            lcolnew[idx++] = (int)(w * 32 + bit);
           }
         }
-        if (lane == 0) misc[MI_M] = M;
-      } else {
-        for (int r = warp - 1; r < nwin; r += NW - 1) {
+        if (lane == 0) ls[LS_M] = M;
+      }
+    } else {
+      int done = 0;
+      for (int g = 0; g < G; ++g) {
+        volatile int* ls = LSp(g);
+        const int nwin = ls[LS_NWIN];
+        if (!ls[LS_ACTIVE]) continue;
+        const int gen = ls[LS_GEN];
+        const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + gen * 4 * B;
+        const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
+        TabEntry* ntab = reinterpret_cast<TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)(gen ^ 1) * B * Kcap;
+        const int* wins = reinterpret_cast<const int*>(lane_base(g) + L.l_wins);
+        for (int r = 0; r < nwin; ++r, ++done) {
+          if (done % (NW - G) != warp - G) continue;
           const int b = wins[r];
           const int Kb = mK[b];
           for (int c = lane; c < Kb; c += 32) ntab[(size_t)r * Kcap + c] = tab[(size_t)b * Kcap + c];
         }
       }
-      named_bar_sync(1, NT);
+    }
+    named_bar_sync(1, NT);
 
-      // ---- P4: patch the one changed table entry per child; back-pointers; hypothesis meta
-      const int M = misc[MI_M];
-      if (tid < nwin) {
-        const int r = tid;
+    // ---- P4: patch the one changed table entry per child; back-pointers; hypothesis meta;
+    //          build the CTA-wide column list
+    int colbase[kMaxLanes], Mtot = 0;
+    for (int g = 0; g < G; ++g) { colbase[g] = Mtot; Mtot += LSp(g)[LS_M]; }
+    if (tid < G * B) {
+      const int g = tid / B, r = tid % B;
+      volatile int* ls = LSp(g);
+      const int nwin = ls[LS_NWIN];
+      if (ls[LS_ACTIVE] && r < nwin) {
+        const int gen = ls[LS_GEN];
+        int* meta = reinterpret_cast<int*>(lane_base(g) + L.l_meta);
+        const int* mK = meta + gen * 4 * B; const int* mLast = mK + B; const int* mTot = mK + 2 * B;
+        int* nK = meta + (gen ^ 1) * 4 * B; int* nLast = nK + B; int* nTot = nK + 2 * B;
+        float* nNl = reinterpret_cast<float*>(nK + 3 * B);
+        const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
+        TabEntry* ntab = reinterpret_cast<TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)(gen ^ 1) * B * Kcap;
+        const int* wins = reinterpret_cast<const int*>(lane_base(g) + L.l_wins);
+        const int* wcol = reinterpret_cast<const int*>(lane_base(g) + L.l_wcol);
+        const int* lcolsrc = reinterpret_cast<const int*>(lane_base(g) + L.l_lcol);
+        const int* lcolnew = lcolsrc + B;
         const int b = wins[r], c = wins[B + r];
+        const float S = reinterpret_cast<const float*>(wins)[2 * B + r];
         const int Kb = mK[b];
         const bool isnew = (c == Kb);
+        const int t = ls[LS_T], TN = ls[LS_TN], N = ls[LS_N];
         if (isnew && Kb >= Kcap) {
-          misc[MI_ERR] = 1;
+          ls[LS_ERR] = 1;  // more clusters than the device tables hold
         } else {
           const TabEntry old = isnew ? TabEntry{kInitSlot, 0, 0, 0} : tab[(size_t)b * Kcap + c];
           const bool moved = isnew || (c != mLast[b]);
+          const int lc = wcol[r];
           TabEntry ne;
-          ne.slot = colnew[col[r]];
-          ne.blocks = old.blocks + (moved ? 1 : 0);  // uisrnn.py:431-432; new cluster starts at 1 (:76)
+          ne.slot = lcolnew[lc];
+          ne.blocks = old.blocks + (moved ? 1 : 0);  // uisrnn.py:431-432; a new cluster starts at 1 (:76)
           ne.visits = old.visits + 1;
           ne.pad = 0;
           ntab[(size_t)r * Kcap + c] = ne;
           nK[r] = Kb + (isnew ? 1 : 0);
           nLast[r] = c;
           nTot[r] = mTot[b] + (moved ? 1 : 0);
-          nNl[r] = reinterpret_cast<float*>(wins)[2 * B + r];
-          if (col[r] >= 0 && colsrc[col[r]] == old.slot) colvis[col[r]] = old.visits;  // same slot => same count
+          nNl[r] = S;
+          const int m = colbase[g] + lc;
+          if (lcolsrc[lc] == old.slot) colvis[m] = old.visits;  // same slot => same visit count
         }
-        if (t >= TN - N) bp[(size_t)(t - (TN - N)) * B + r] = ((unsigned)b << 16) | (unsigned)c;
-        if (traced && p.dbg_win && dbg_rows + r < p.trace_capacity) {
-          p.dbg_win[(dbg_rows + r) * 2 + 0] = b;
-          p.dbg_win[(dbg_rows + r) * 2 + 1] = c;
-          p.dbg_score[dbg_rows + r] = reinterpret_cast<float*>(wins)[2 * B + r];
+        if (t >= TN - N) bp_cta[((size_t)g * p.maxN + (t - (TN - N))) * B + r] = ((unsigned)b << 16) | (unsigned)c;
+        if (ls[LS_TRACED]) {
+          const long long rows = ((long long)ls[LS_DBGROWS_HI] << 32) | (unsigned)ls[LS_DBGROWS_LO];
+          if (p.dbg_win && rows + r < p.trace_capacity) {
+            p.dbg_win[(rows + r) * 2 + 0] = b;
+            p.dbg_win[(rows + r) * 2 + 1] = c;
+            p.dbg_score[rows + r] = S;
+          }
+          if (r == 0 && p.dbg_off) p.dbg_off[t + 1] = rows + nwin;
         }
       }
-      if (traced && tid == 0 && p.dbg_off) p.dbg_off[t + 1] = dbg_rows + nwin;
-      dbg_rows += nwin;
-      if (tid == 0) {
-        st_cand += NE; st_cols += M; st_steps += 1;
-        const int npass = max(1, (M + MP - 1) / MP);
-        st_pass += npass;
-        if (npass > 1) { __threadfence_block(); misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + (npass - 1); }
+    }
+    for (int f = tid; f < Mtot; f += NT) {  // column list: lane-local -> CTA-wide
+      int g = 0;
+      while (g + 1 < G && f >= colbase[g + 1]) ++g;
+      const int lc = f - colbase[g];
+      const int* lcolsrc = reinterpret_cast<const int*>(lane_base(g) + L.l_lcol);
+      collane[f] = g;
+      colsrc[f] = lcolsrc[lc];
+      colnew[f] = lcolsrc[B + lc];
+      colgi[f] = (int)((L.lanes + (size_t)g * L.lane_stride + L.l_gi) / 4) + (LSp(g)[LS_T] & 1) * 3 * H;
+    }
+    const int npass = max(1, (Mtot + kCP - 1) / kCP);
+    if (tid == 0) {
+      for (int g = 0; g < G; ++g) {
+        volatile int* ls = LSp(g);
+        if (ls[LS_ACTIVE]) { st_cand += ls[LS_NE]; st_steps += 1; }
+      }
+      st_cols += Mtot;
+      st_pass += npass;
+      if (npass > 1) { __threadfence_block(); misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + (npass - 1); }
+    }
+    named_bar_sync(1, NT);
+
+    UIS_PHASE(0);
+    // ---- P5: GRU + MLP for the Mtot distinct source states, kCP columns per weight pass
+    if (Mtot == 0) drain_pass<C>(full, empty, it, lane);
+    for (int m0 = 0; m0 < Mtot; m0 += kCP) {
+      const int Mp = min(kCP, Mtot - m0);
+      // gather the source hidden states, transposed: XA[k][m]
+#pragma unroll
+      for (int u = 0; u < UPT; ++u) {
+        const int j = tid + NT * u;
+#pragma unroll
+        for (int c = 0; c < kCP / 4; ++c) {
+          float hv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int m = 4 * c + q;
+            hv[q] = (m < Mp) ? pool_hidden_cta[(size_t)collane[m0 + m] * pool_h_stride +
+                                               (size_t)colsrc[m0 + m] * H + j]
+                             : 0.f;
+          }
+          reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        }
       }
       named_bar_sync(1, NT);
-      if (misc[MI_ERR]) {
-        // cluster cap exceeded: the already-published weight pass must still be consumed
-        failed = true;
+      UIS_PHASE(1);
+      const int nc = (Mp + 3) / 4;
+      if (nc == 1) run_pass<C, 1>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      else if (nc == 2) run_pass<C, 2>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      else if (nc == 3) run_pass<C, 3>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      else run_pass<C, 4>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      named_bar_sync(1, NT);
+      UIS_PHASE(4);
+    }
+
+    // ---- P6: advance every lane; finished utterances are back-tracked and replaced
+    int fin[kMaxLanes];
+    for (int g = 0; g < G; ++g) {
+      volatile int* ls = LSp(g);
+      const bool act = ls[LS_ACTIVE] != 0;
+      const bool failed = act && ls[LS_ERR] != 0;
+      fin[g] = act && (failed || ls[LS_NWIN] == 0 || ls[LS_T] + 1 >= ls[LS_TN]);
+      if (tid == 0 && act) {
+        const int* nK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + (ls[LS_GEN] ^ 1) * 4 * B;
+        for (int r = 0; r < ls[LS_NWIN]; ++r) st_maxk = max(st_maxk, nK[r]);
       }
-
-      // ---- P5: GRU + MLP for the M distinct source states, MP columns per weight pass
-      if (M == 0) drain_pass<H, D>(full, empty, it, lane);
-      for (int m0 = 0; m0 < M; m0 += MP) {
-        const int Mp = min(MP, M - m0);
-        {  // gather source hidden states, transposed: XA[k][m]
-          float hv[MP];
-#pragma unroll
-          for (int m = 0; m < MP; ++m)
-            hv[m] = (m < Mp) ? pool_hidden[(size_t)colsrc[m0 + m] * H + j] : 0.f;
-#pragma unroll
-          for (int c = 0; c < MP / 4; ++c)
-            reinterpret_cast<float4*>(XA + (size_t)j * MP)[c] =
-                make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
-        }
-        named_bar_sync(1, NT);
-        const int nc = (Mp + 3) / 4;
-        if (nc == 1) gru_pass<H, D, MP, 1>(ring, full, empty, it, XA, XB, gs, bhr, bhz, bhn, Mp, colnew + m0, pool_hidden, j, lane);
-        else if (nc == 2) gru_pass<H, D, MP, 2>(ring, full, empty, it, XA, XB, gs, bhr, bhz, bhn, Mp, colnew + m0, pool_hidden, j, lane);
-        else gru_pass<H, D, MP, 3>(ring, full, empty, it, XA, XB, gs, bhr, bhz, bhn, Mp, colnew + m0, pool_hidden, j, lane);
-        named_bar_sync(1, NT);
-        if (nc == 1) mlp1_pass<H, D, MP, 1>(ring, full, empty, it, XB, XA, b1j, j, lane);
-        else if (nc == 2) mlp1_pass<H, D, MP, 2>(ring, full, empty, it, XB, XA, b1j, j, lane);
-        else mlp1_pass<H, D, MP, 3>(ring, full, empty, it, XB, XA, b1j, j, lane);
-        named_bar_sync(1, NT);
-        if (nc == 1) mlp2_pass<H, D, MP, 1>(ring, full, empty, it, XA, XB, b2d, Mp, colsrc + m0, colnew + m0, colvis + m0, pool_mean, tid, lane);
-        else if (nc == 2) mlp2_pass<H, D, MP, 2>(ring, full, empty, it, XA, XB, b2d, Mp, colsrc + m0, colnew + m0, colvis + m0, pool_mean, tid, lane);
-        else mlp2_pass<H, D, MP, 3>(ring, full, empty, it, XA, XB, b2d, Mp, colsrc + m0, colnew + m0, colvis + m0, pool_mean, tid, lane);
-        named_bar_sync(1, NT);
+    }
+    for (int g = 0; g < G; ++g) {  // debug taps of finishing lanes (all threads)
+      if (!fin[g]) continue;
+      volatile int* ls = LSp(g);
+      const int u = ls[LS_U], nwin = ls[LS_NWIN], ngen = ls[LS_GEN] ^ 1;
+      const bool ok = !ls[LS_ERR] && nwin > 0;
+      const int* fK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + ngen * 4 * B;
+      const float* fNl = reinterpret_cast<const float*>(fK + 3 * B);
+      if (p.dbg_final_scores) {
+        if (tid < B) p.dbg_final_scores[(size_t)u * B + tid] = (ok && tid < nwin) ? fNl[tid] : INF;
+        if (tid == 0 && p.dbg_final_k) p.dbg_final_k[u] = ok ? fK[0] : 0;
       }
-      if (tid == 0) { for (int r = 0; r < nwin; ++r) st_maxk = max(st_maxk, nK[r]); }
-      nb = nwin;
-      gen ^= 1;
-      if (failed || nb == 0) break;
-    }  // steps
-
-    // drain a pending prefetch before the buffers are reused by the next utterance
-    cp_async_wait_all();
-    named_bar_sync(1, NT);
-
-    // ---- utterance epilogue: back-track the best hypothesis (uisrnn.py:561)
-    if (tid == 0) {
-      if (failed || nb == 0) {
-        p.status[u] = failed ? -4 : -1;
-        for (int i = 0; i < N; ++i) p.labels[row0 + i] = -1;
-      } else {
-        p.status[u] = 0;
-        int r = 0;
-        for (int i = N - 1; i >= 0; --i) {
-          const unsigned e = bp[(size_t)i * B + r];
-          p.labels[row0 + i] = (int)(e & 0xffffu);
-          r = (int)(e >> 16);
+      if (ls[LS_TRACED] && ok && p.dbg_best_mean) {
+        const TabEntry* ftab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)ngen * B * Kcap;
+        for (int c = 0; c < fK[0]; ++c) {  // best hypothesis = rank 0
+          const TabEntry en = ftab[c];
+          if (tid < D) p.dbg_best_mean[(size_t)c * D + tid] = pool_mean_cta[g * pool_m_stride + (size_t)en.slot * D + tid];
+          for (int uu = 0; uu < UPT; ++uu)
+            p.dbg_best_hidden[(size_t)c * H + tid + NT * uu] =
+                pool_hidden_cta[g * pool_h_stride + (size_t)en.slot * H + tid + NT * uu];
+          if (tid == 0) p.dbg_best_blocks[c] = en.blocks;
         }
       }
     }
-    if (p.dbg_final_scores) {
-      const float* fNl = reinterpret_cast<const float*>(meta + gen * 4 * B + 3 * B);
-      if (tid < B) p.dbg_final_scores[(size_t)u * B + tid] = (tid < nb) ? fNl[tid] : __int_as_float(0x7f800000);
-      if (tid == 0 && p.dbg_final_k) p.dbg_final_k[u] = (nb > 0) ? meta[gen * 4 * B] : 0;
-    }
-    if (traced && nb > 0 && !failed && p.dbg_best_mean) {
-      const TabEntry* ftab = tabs + (size_t)gen * B * Kcap;  // best hypothesis = rank 0
-      const int K0 = meta[gen * 4 * B];
-      for (int c = 0; c < K0; ++c) {
-        const TabEntry en = ftab[c];
-        if (tid < D) p.dbg_best_mean[(size_t)c * D + tid] = pool_mean[(size_t)en.slot * D + tid];
-        p.dbg_best_hidden[(size_t)c * H + j] = pool_hidden[(size_t)en.slot * H + j];
-        if (tid == 0) p.dbg_best_blocks[c] = en.blocks;
+    named_bar_sync(1, NT);
+    if (tid < G) {
+      const int g = tid;
+      volatile int* ls = LSp(g);
+      if (ls[LS_ACTIVE]) {
+        if (fin[g]) {  // utterance epilogue: back-track the best hypothesis (uisrnn.py:561)
+          const int u = ls[LS_U], N = ls[LS_N];
+          const long long row0 = ((long long)ls[LS_ROW0_HI] << 32) | (unsigned)ls[LS_ROW0_LO];
+          if (ls[LS_ERR] || ls[LS_NWIN] == 0) {
+            p.status[u] = ls[LS_ERR] ? -4 : -1;
+            for (int i = 0; i < N; ++i) p.labels[row0 + i] = -1;
+          } else {
+            p.status[u] = 0;
+            const unsigned* bp = bp_cta + (size_t)g * p.maxN * B;
+            int r = 0;
+            for (int i = N - 1; i >= 0; --i) {
+              const unsigned e = bp[(size_t)i * B + r];
+              p.labels[row0 + i] = (int)(e & 0xffffu);
+              r = (int)(e >> 16);
+            }
+          }
+          lane_fetch(g);
+        } else {
+          const long long rows = (((long long)ls[LS_DBGROWS_HI] << 32) | (unsigned)ls[LS_DBGROWS_LO]) + ls[LS_NWIN];
+          ls[LS_DBGROWS_LO] = (int)(rows & 0xffffffffll); ls[LS_DBGROWS_HI] = (int)(rows >> 32);
+          ls[LS_T] = ls[LS_T] + 1; ls[LS_NB] = ls[LS_NWIN]; ls[LS_GEN] = ls[LS_GEN] ^ 1; ls[LS_FRESH] = 0;
+        }
       }
     }
     named_bar_sync(1, NT);
-  }  // utterances
+    {
+      bool any = false;
+      for (int g = 0; g < G; ++g)
+        if (fin[g] && LSp(g)[LS_ACTIVE] && LSp(g)[LS_FRESH]) { lane_prefetch(g, 0); any = true; }
+      if (any) cp_async_commit();
+    }
+    UIS_PHASE(5);
+  }  // CTA steps
 
+  cp_async_wait_all();
   if (tid == 0) {
     __threadfence_block();
     misc[MI_DONE] = 1;
@@ -712,6 +902,7 @@ __global__ void __launch_bounds__(H + 32, 1) uis_beam_kernel(const BeamParams p)
     atomicAdd(&p.stats[2], st_cand);
     atomicAdd(&p.stats[3], st_steps);
     atomicMax(&p.stats[4], (unsigned long long)st_maxk);
+    for (int i = 0; i < 6; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }
 }
 
