@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -251,6 +252,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.x = x_dev; p.gi = m->gi.as<float>();
   p.row_off = m->row_off.as<long long>(); p.order = m->order.as<int>();
   p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN; p.G = pl.G;
+  { const char* e = getenv("UIS_DBG_MODE"); p.dbg_mode = e ? atoi(e) : 0; }
   p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>();
   p.bp = m->bp.as<unsigned>();
   p.queue = m->queue_stats.as<int>();

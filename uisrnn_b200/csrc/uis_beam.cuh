@@ -66,6 +66,7 @@ struct BeamParams {
   const long long* row_off; // [U + 1]
   const int* order;         // [U] utterance ids, longest first
   int U, B, Kcap, T, P, maxN, G;
+  int dbg_mode;  // 0 normal; 1 = stream the weights but skip the math (timing experiment, results invalid)
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
   float* pool_hidden;  // [ctas*G][P][H]
@@ -811,7 +812,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
       named_bar_sync(1, NT);
       UIS_PHASE(1);
       const int nc = (Mp + 3) / 4;
-      if (nc == 1) run_pass<C, 1>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane);
+      else if (nc == 1) run_pass<C, 1>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       else if (nc == 2) run_pass<C, 2>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       else if (nc == 3) run_pass<C, 3>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       else run_pass<C, 4>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
