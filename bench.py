@@ -258,9 +258,28 @@ def run_b200(args):
   dev_ms = ev0.elapsed_time(ev1)
   labels_first = labels_dev.cpu().numpy().copy()
 
-  # ---- end-to-end leg (`e2e`): host float64 buffers (pinned) -> C ABI -> host int32 labels
+  # ---- end-to-end leg (`e2e`): the public API a user calls -- uisrnn.UISRNN.predict(list of host
+  #      float64 arrays) -> list of label lists.  Pinned host inputs; H2D, cast, GEMM, beam search,
+  #      D2H and the Python list conversion are all inside the timed region.
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import uisrnn
+  margs, _, iargs = uisrnn.parse_arguments([])
+  margs.verbosity, margs.transition_bias, margs.crp_alpha = 0, float(weights['transition_bias']), float(weights['crp_alpha'])
+  api_model = uisrnn.UISRNN(margs)
+  assert api_model.device.type == 'cuda'
+  if local != 0:
+    api_model.device = torch.device('cuda', local)
+  sd = {'gru.weight_ih_l0': weights['weight_ih_l0'], 'gru.weight_hh_l0': weights['weight_hh_l0'],
+        'gru.bias_ih_l0': weights['bias_ih_l0'], 'gru.bias_hh_l0': weights['bias_hh_l0'],
+        'linear_mean1.weight': weights['w1'], 'linear_mean1.bias': weights['b1'],
+        'linear_mean2.weight': weights['w2'], 'linear_mean2.bias': weights['b2']}
+  api_model.rnn_model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+  api_model.rnn_init_hidden = torch.nn.Parameter(torch.from_numpy(np.array(weights['h0'])))
+  api_model.sigma2 = torch.nn.Parameter(torch.from_numpy(np.array(weights['sigma2'])))
+  iargs.beam_size, iargs.look_ahead, iargs.test_iteration = BEAM, LOOK_AHEAD, TEST_ITER
+
   def step_e2e():
-    return model.predict(seqs, beam_size=BEAM, look_ahead=LOOK_AHEAD, test_iteration=TEST_ITER, stream=stream)
+    return api_model.predict(seqs, iargs)
 
   for _ in range(max(1, args.warmup // 2)):
     out = step_e2e()
@@ -271,7 +290,8 @@ def run_b200(args):
   torch.cuda.synchronize()
   e2e_s = time.perf_counter() - t0
   clocks = sampler.stop() if rank == 0 else None
-  assert np.array_equal(np.concatenate(out), labels_first), 'e2e and device-resident legs disagree'
+  assert np.array_equal(np.concatenate([np.asarray(o, dtype=np.int32) for o in out]), labels_first), \
+      'e2e and device-resident legs disagree'
 
   t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
   if world > 1:
@@ -305,7 +325,7 @@ def run_b200(args):
                  'l2': 'inputs larger than L2: x %.0f MB + gi %.0f MB rewritten every step' % (
                      frames * D * 4 / 1e6, frames * 3 * H * 4 / 1e6)},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': frames * D * 8, 'd2h_bytes_per_step': frames * 4,
-              'path': 'uis_predict() C ABI: pinned host float64 -> H2D -> cast+GEMM+beam kernels -> D2H int32 labels'},
+              'path': 'uisrnn.UISRNN.predict(list of pinned float64 ndarrays) -> uis_predict() C ABI: H2D, cast+GEMM+beam kernels, D2H int32 labels -> Python lists'},
       'gpu_launches': int(args.steps * 2),
       'clocks': clocks,
       'roofline': {'bound': 'hbm', 'kernel': 'uis_beam_kernel<512,256,12>', 'achieved': achieved, 'peak': peak,

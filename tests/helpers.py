@@ -78,3 +78,34 @@ def compare_trace(win, score, off, gwin, gscore, goff, rtol=1e-5):
           swaps += 1
     prev_a, prev_b = a, b
   return swaps
+
+
+def uisrnn_from_weights(weights, enable_cuda=False, verbosity=0):
+  """Builds a `uisrnn.UISRNN` (this repo's drop-in package) holding golden-fixture weights."""
+  import torch
+  import uisrnn
+  model_args, _, _ = uisrnn.parse_arguments([])
+  model_args.observation_dim = int(weights['w2'].shape[0])
+  model_args.rnn_hidden_size = int(weights['w1'].shape[0])
+  model_args.rnn_depth = int(weights['depth'])
+  model_args.enable_cuda = enable_cuda
+  model_args.verbosity = verbosity
+  model_args.transition_bias = float(weights['transition_bias'])
+  model_args.crp_alpha = float(weights['crp_alpha'])
+  model = uisrnn.UISRNN(model_args)
+  sd = {'linear_mean1.weight': weights['w1'], 'linear_mean1.bias': weights['b1'],
+        'linear_mean2.weight': weights['w2'], 'linear_mean2.bias': weights['b2']}
+  for layer in range(model_args.rnn_depth):
+    for name in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'):
+      sd['gru.{}_l{}'.format(name, layer)] = weights['{}_l{}'.format(name, layer)]
+  model.rnn_model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+  model.rnn_init_hidden = torch.nn.Parameter(torch.from_numpy(np.array(weights['h0'])).to(model.device))
+  model.sigma2 = torch.nn.Parameter(torch.from_numpy(np.array(weights['sigma2'])).to(model.device))
+  return model
+
+
+def inference_args(beam_size=10, look_ahead=1, test_iteration=2):
+  import uisrnn
+  _, _, args = uisrnn.parse_arguments([])
+  args.beam_size, args.look_ahead, args.test_iteration = beam_size, look_ahead, test_iteration
+  return args

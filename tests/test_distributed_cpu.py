@@ -1,0 +1,51 @@
+"""N > 1 path on CPU: utterance sharding over ranks (gloo, world_size 2) gives exactly the
+single-process result; the partition is balanced and order-preserving."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from helpers import ROOT, inference_args, load_weights, uisrnn_from_weights
+
+
+def test_shard_by_frames_is_a_balanced_partition():
+  from uisrnn_b200.uisrnn import shard_by_frames
+  rng = np.random.default_rng(0)
+  lengths = rng.integers(1, 500, size=101).tolist()
+  for n in (1, 2, 3, 8):
+    shards = shard_by_frames(lengths, n)
+    assert sorted(i for s in shards for i in s) == list(range(101))
+    loads = [sum(lengths[i] for i in s) for s in shards]
+    assert max(loads) - min(loads) <= max(lengths)
+    assert all(s == sorted(s) for s in shards)
+  assert shard_by_frames([], 4) == [[], [], [], []]
+
+
+def _worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import torch.distributed as dist
+  from uisrnn_b200.distributed import predict_sharded
+  from uisrnn_b200.synth import synth_utt
+  dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+  model = uisrnn_from_weights(load_weights('model_small.npz'))
+  seqs = [synth_utt(700 + i, n_frames=10 + 3 * i, dim=64, n_spk=2, noise=0.08)[0] for i in range(5)]
+  merged = predict_sharded(model, seqs, inference_args(beam_size=4))
+  np.save(os.path.join(out_dir, 'rank%d.npy' % rank), np.array(merged, dtype=object), allow_pickle=True)
+  dist.destroy_process_group()
+
+
+def test_predict_sharded_gloo_world2(tmp_path):
+  with socket.socket() as s:
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+  mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  from uisrnn_b200.synth import synth_utt
+  model = uisrnn_from_weights(load_weights('model_small.npz'))
+  seqs = [synth_utt(700 + i, n_frames=10 + 3 * i, dim=64, n_spk=2, noise=0.08)[0] for i in range(5)]
+  want = model.predict(seqs, inference_args(beam_size=4))
+  for rank in (0, 1):
+    got = np.load(str(tmp_path / ('rank%d.npy' % rank)), allow_pickle=True).tolist()
+    assert [list(g) for g in got] == want

@@ -1,0 +1,30 @@
+"""Multi-process (one process per GPU) utterance sharding for predict().
+
+The path shards naturally: every test utterance is an independent beam search (the reference
+maps `predict_single` over the list, `/root/reference/uisrnn/uisrnn.py:587-589, 619-621`), so the
+only cross-rank traffic is the gather of the label lists -- no data-path collective.  Works with
+any `torch.distributed` backend (NCCL on the GPU box, gloo in the CPU tests).
+"""
+import torch.distributed as dist
+
+from .uisrnn import shard_by_frames
+
+
+def predict_sharded(model, test_sequences, args, group=None):
+  """Every rank passes the same list; rank r decodes the r-th shard (longest-first partition by
+  frame count) with `model.predict`, and every rank returns the complete, ordered result."""
+  if not isinstance(test_sequences, list):
+    raise TypeError('test_sequences must be a list.')
+  if not (dist.is_available() and dist.is_initialized()):
+    return model.predict(test_sequences, args)
+  world = dist.get_world_size(group)
+  rank = dist.get_rank(group)
+  shards = shard_by_frames([len(s) for s in test_sequences], world)
+  mine = model.predict([test_sequences[i] for i in shards[rank]], args) if shards[rank] else []
+  gathered = [None] * world
+  dist.all_gather_object(gathered, mine, group=group)
+  merged = [None] * len(test_sequences)
+  for shard, labels in zip(shards, gathered):
+    for i, lab in zip(shard, labels):
+      merged[i] = lab
+  return merged
