@@ -84,8 +84,9 @@ typedef struct uis_stats {
   float beam_ms;           /* device time of the persistent beam-search kernel                 */
   int32_t lanes;           /* lanes per CTA used                                               */
   int32_t reserved;
-  int64_t phase_cycles[6]; /* SM cycles summed over CTAs: select(score+rank+re-pack), gather,
-                              GRU pass, W1 pass, W2 pass, advance/back-track                   */
+  int64_t phase_cycles[10]; /* SM cycles summed over CTAs: [0] re-pack (P4), [1] gather, [2] GRU pass,
+                               [3] W1 pass, [4] W2 pass, [5] advance/back-track, [6] frame landing
+                               (P0), [7] scoring (P1), [8] ranking (P2), [9] column/slot assignment (P3) */
 } uis_stats;
 
 int uis_version(void);

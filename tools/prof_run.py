@@ -20,4 +20,4 @@ ph = np.array(st['phase_cycles'], dtype=np.float64)
 tot = ph.sum()
 print({k: v for k, v in st.items() if k != 'phase_cycles'})
 print('frames/s %.0f  us/pass/cta %.1f  cols/pass %.2f' % (U * N / (st['beam_ms'] / 1e3), st['beam_ms'] * 1e3 * st['ctas'] / st['weight_passes'], st['gru_columns'] / st['weight_passes']))
-print('phase share: select %.3f gather %.3f gru %.3f w1 %.3f w2 %.3f advance %.3f | cycles/pass: ' % tuple(ph / tot), (ph / st['weight_passes']).round(0))
+print('phase share: repack %.3f gather %.3f gru %.3f w1 %.3f w2 %.3f advance %.3f land %.3f score %.3f rank %.3f assign %.3f | cycles/pass: ' % tuple(ph / tot), (ph / st['weight_passes']).round(0))

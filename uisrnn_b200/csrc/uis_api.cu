@@ -99,7 +99,7 @@ int launch_beam(const uis::BeamParams& p, int ctas, cudaStream_t st) {
                 p.B, p.Kcap, p.G, L.total);
   auto kern = uis::uis_beam_kernel<H, D>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  kern<<<ctas, uis::Cfg<H, D>::NT + 32, L.total, st>>>(p);
+  kern<<<ctas, uis::Cfg<H, D>::BLOCK, L.total, st>>>(p);
   CU(cudaGetLastError());
   return 0;
 }
@@ -172,7 +172,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   pl->L = o->look_ahead;
   pl->T = o->test_iteration;
   pl->Kcap = o->kcap > 0 ? o->kcap : 32;
-  if (pl->Kcap > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
+  if (pl->Kcap > 2047 || pl->B * pl->Kcap + pl->B + 1 > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
   pl->P = pl->B * pl->Kcap + pl->B + 1;
   pl->rows = U > 0 ? off[U] : 0;
   int maxN = 0;
@@ -333,9 +333,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 int collect(uis_model* m) {
   if (!m->stats_pending) return 0;
   CU(cudaStreamSynchronize(m->last_stream));
-  unsigned long long s[16];
+  unsigned long long s[20];
   CU(cudaMemcpy(s, m->queue_stats.as<unsigned long long>() + 8, sizeof s, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 6; ++i) m->stats.phase_cycles[i] = (int64_t)s[8 + i];
+  for (int i = 0; i < 10; ++i) m->stats.phase_cycles[i] = (int64_t)s[8 + i];
   m->stats.gru_columns = (int64_t)s[0];
   m->stats.weight_passes = (int64_t)s[1];
   m->stats.candidates = (int64_t)s[2];

@@ -33,8 +33,8 @@
 
 namespace uis {
 
-constexpr int kStages = 4;              // weight ring depth
-constexpr int kStageBytes = 24 * 1024;  // bytes per ring stage
+constexpr int kStages = 2;              // weight ring depth
+constexpr int kStageBytes = 48 * 1024;  // bytes per ring stage
 constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
 constexpr int kCP = 16;                 // GRU columns per weight pass
 constexpr int kMaxLanes = 4;
@@ -100,6 +100,13 @@ struct Cfg {
   static constexpr int UPT = (H >= 512) ? 2 : 1;  // hidden units per consumer thread
   static constexpr int NT = H / UPT;              // consumer threads
   static constexpr int NW = NT / 32;
+  // Register re-balancing (setmaxnreg): with 8 consumer warps the launch allocation caps every
+  // thread at 168 registers; a 4-warp producer group that shrinks itself to 24 registers lets
+  // the two consumer warpgroups grow to 240 (6x16 accumulator tile + operand double-buffering
+  // without spills).  Small configs (NT < 256) already have 255 registers per thread.
+  static constexpr bool REBALANCE = (NT == 256);
+  static constexpr int PRODUCER_THREADS = REBALANCE ? 128 : 32;
+  static constexpr int BLOCK = NT + PRODUCER_THREADS;
   static constexpr int RG = 3 * UPT;              // GRU pass: rows per thread
   static constexpr int KG1 = UPT, TG1 = NT / KG1, R1 = H / TG1;             // W1 pass: K-groups, rows/thread
   static constexpr int R2 = (UPT == 2) ? 4 : 1, KG2 = NT * R2 / D, TG2 = NT / KG2;  // W2 pass
@@ -208,46 +215,91 @@ __device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsi
 // ------------------------------------------------------------------ consumer: one weight matrix
 // acc[i][m] += sum_k Wt[k][tl + TG*i] * X[k][m]   for this thread's R rows and its K-group's
 // share (KT/KG k-rows) of every ring tile.  Wt tiles are [KT][ROWS] floats; X is [H][kCP].
+// The operand loads are software-pipelined ACROSS ring tiles: the first k-step of tile t+1 is
+// fetched (after its full-barrier test) before the last k-step of tile t is multiplied, so the
+// mbarrier round trip and the shared-memory latency are not exposed at every tile boundary.
+template <int R, int NC>
+struct Operands {
+  float w[R];
+  float4 x[NC];
+};
+
 template <class C, int ROWS, int KT, int KG, int R, int NC>
 __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
                                          unsigned& it, const float* __restrict__ X, float (&acc)[R][4 * NC],
                                          int tid, int lane) {
   constexpr int TG = C::NT / KG;
   constexpr int KPG = KT / KG;
+  constexpr int NTILES = C::H / KT;
   const int kg = tid / TG, tl = tid % TG;
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
     for (int m = 0; m < 4 * NC; ++m) acc[i][m] = 0.f;
-  for (int tile = 0; tile < C::H / KT; ++tile, ++it) {
-    const unsigned s = it % kStages, ph = (it / kStages) & 1;
-    mbar_wait(&full[s], ph);
-    const float* wt = ring + (size_t)s * (kStageBytes / 4) + (size_t)(kg * KPG) * ROWS + tl;
-    const float4* xp = reinterpret_cast<const float4*>(X + (size_t)(tile * KT + kg * KPG) * kCP);
-#pragma unroll 4
-    for (int kq = 0; kq < KPG; ++kq) {
-      float w[R];
+
+  auto tile_w = [&](unsigned itx) -> const float* {
+    return ring + (size_t)(itx % kStages) * (kStageBytes / 4) + (size_t)(kg * KPG) * ROWS + tl;
+  };
+  auto tile_x = [&](int tile) -> const float4* {
+    return reinterpret_cast<const float4*>(X + (size_t)(tile * KT + kg * KPG) * kCP);
+  };
+  // volatile ld.shared: keeps the loads of k-step s+1 AHEAD of the FFMA2s of k-step s in the
+  // instruction stream (the compiler otherwise sinks them next to their first use, which
+  // exposes the ~30-cycle shared-memory latency with only 2 warps per scheduler)
+  auto load = [&](Operands<R, NC>& o, const float* wt, const float4* xp, int kq) {
+    const uint32_t wa = smem_u32(wt) + (uint32_t)(kq * ROWS) * 4u;
+    const uint32_t xa = smem_u32(xp) + (uint32_t)(kq * (kCP / 4)) * 16u;
 #pragma unroll
-      for (int i = 0; i < R; ++i) w[i] = wt[kq * ROWS + TG * i];
+    for (int i = 0; i < R; ++i)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.w[i]) : "r"(wa + (uint32_t)(TG * i) * 4u));
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float4 x = xp[kq * (kCP / 4) + c];
-        const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
+    for (int c = 0; c < NC; ++c)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o.x[c].x), "=f"(o.x[c].y), "=f"(o.x[c].z), "=f"(o.x[c].w)
+                   : "r"(xa + (uint32_t)c * 16u));
+  };
+  auto mac = [&](const Operands<R, NC>& o) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-          // packed fp32 FMA (sm_100 FFMA2): two IEEE-RN fmas per instruction, w broadcast
-          const float2 w2 = make_float2(w[i], w[i]);
-          float2 a0 = make_float2(acc[i][4 * c + 0], acc[i][4 * c + 1]);
-          float2 a1 = make_float2(acc[i][4 * c + 2], acc[i][4 * c + 3]);
-          a0 = __ffma2_rn(xlo, w2, a0);
-          a1 = __ffma2_rn(xhi, w2, a1);
-          acc[i][4 * c + 0] = a0.x; acc[i][4 * c + 1] = a0.y;
-          acc[i][4 * c + 2] = a1.x; acc[i][4 * c + 3] = a1.y;
-        }
+    for (int c = 0; c < NC; ++c) {
+      const float2 xlo = make_float2(o.x[c].x, o.x[c].y), xhi = make_float2(o.x[c].z, o.x[c].w);
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        // packed fp32 FMA (sm_100 FFMA2): two IEEE-RN fmas per instruction, w broadcast
+        const float2 w2 = make_float2(o.w[i], o.w[i]);
+        float2 a0 = make_float2(acc[i][4 * c + 0], acc[i][4 * c + 1]);
+        float2 a1 = make_float2(acc[i][4 * c + 2], acc[i][4 * c + 3]);
+        a0 = __ffma2_rn(xlo, w2, a0);
+        a1 = __ffma2_rn(xhi, w2, a1);
+        acc[i][4 * c + 0] = a0.x; acc[i][4 * c + 1] = a0.y;
+        acc[i][4 * c + 2] = a1.x; acc[i][4 * c + 3] = a1.y;
       }
+    }
+  };
+
+  Operands<R, NC> cur, nxt;
+  mbar_wait(&full[it % kStages], (it / kStages) & 1);
+  const float* wt = tile_w(it);
+  const float4* xp = tile_x(0);
+  load(cur, wt, xp, 0);
+  for (int tile = 0; tile < NTILES; ++tile) {
+    const unsigned s = it % kStages;
+#pragma unroll
+    for (int kq = 0; kq < KPG; ++kq) {
+      if (kq + 1 < KPG) {
+        load(nxt, wt, xp, kq + 1);
+      } else if (tile + 1 < NTILES) {
+        const unsigned itn = it + 1;
+        mbar_wait(&full[itn % kStages], (itn / kStages) & 1);
+        wt = tile_w(itn);
+        xp = tile_x(tile + 1);
+        load(nxt, wt, xp, 0);
+      }
+      mac(cur);
+      cur = nxt;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    ++it;
   }
 }
 
@@ -393,7 +445,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
 
 // ------------------------------------------------------------------ the kernel
 template <int H, int D>
-__global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const BeamParams p) {
+__global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const BeamParams p) {
   using C = Cfg<H, D>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -421,10 +473,12 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
   }
   __syncthreads();
 
-  if (warp == NW) {  // ---------------- producer warp
-    if (lane == 0) producer_loop<C>(p, ring, full, empty, misc);
+  if (warp >= NW) {  // ---------------- producer warp (+ idle warps of its warpgroup)
+    if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == NW && lane == 0) producer_loop<C>(p, ring, full, empty, misc);
     return;
   }
+  if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
 
   // ---------------- consumer threads (tid < NT); they synchronise on named barrier 1
   auto lane_base = [&](int g) -> unsigned char* { return smem + L.lanes + (size_t)g * L.lane_stride; };
@@ -457,7 +511,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
   unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;
   int st_maxk = 0;
   // per-phase cycle counters (thread 0 only): select, gather, gru, w1, w2, advance
-  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tmark = clock64();
 #define UIS_PHASE(i)                         \
   do {                                       \
@@ -544,6 +598,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
     }
     cp_async_wait_all();
     named_bar_sync(1, NT);
+    UIS_PHASE(6);
     for (int g = 0; g < G; ++g) {  // prefetch the next frame of every running lane
       volatile int* ls = LSp(g);
       if (ls[LS_ACTIVE] && ls[LS_T] + 1 < ls[LS_TN]) lane_prefetch(g, ls[LS_T] + 1);
@@ -555,47 +610,105 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
     {
       int ne_g[kMaxLanes], ne_tot = 0;
       for (int g = 0; g < G; ++g) { ne_g[g] = LSp(g)[LS_NE]; ne_tot += ne_g[g]; }
-      for (int f = warp; f < ne_tot; f += NW) {
+      // P1a: one thread per candidate resolves (hypothesis, cluster) -> slot, marks the slot
+      // live, and evaluates the transition / ddCRP term in fp64 from the host-built log tables
+      // (the np.log values of uisrnn.py:415-420, 444-446).  Parked in keys[] / svals[].
+      for (int f = tid; f < ne_tot; f += NT) {
         int g = 0, e = f;
         while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
         volatile int* ls = LSp(g);
         const int gen = ls[LS_GEN];
         const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + gen * 4 * B;
         const int* mLast = mK + B; const int* mTot = mK + 2 * B;
-        const float* mNl = reinterpret_cast<const float*>(mK + 3 * B);
         const int* candoff = reinterpret_cast<const int*>(lane_base(g) + L.l_candoff);
         const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
         int b = 0;
         while (candoff[b + 1] <= e) ++b;
         const int c = e - candoff[b];
-        const int Kb = mK[b];
-        const TabEntry en = (c < Kb) ? tab[(size_t)b * Kcap + c] : TabEntry{kInitSlot, 0, 0, 0};
-        const float* mu = pool_mean_cta + g * pool_m_stride + (size_t)en.slot * D;
-        const float* xs = reinterpret_cast<const float*>(lane_base(g) + L.l_xt) + (ls[LS_T] & 1) * D;
-        // weighted_mse_loss for one row (loss_func.py:33-41): sum_d fl(fl(diff^2) * w_d)
-        float acc = 0.f, d0sq = 1.f;
-        for (int d = lane * 4; d < D; d += 128) {
-          const float4 m4 = *reinterpret_cast<const float4*>(mu + d);
-          const float4 x4 = *reinterpret_cast<const float4*>(xs + d);
-          const float4 w4 = *reinterpret_cast<const float4*>(wv + d);
-          const float e0 = __fsub_rn(m4.x, x4.x), e1 = __fsub_rn(m4.y, x4.y);
-          const float e2 = __fsub_rn(m4.z, x4.z), e3 = __fsub_rn(m4.w, x4.w);
-          const float q0 = __fmul_rn(e0, e0);
-          if (d == 0) d0sq = q0;
-          acc = __fadd_rn(acc, __fmul_rn(q0, w4.x));
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(e1, e1), w4.y));
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(e2, e2), w4.z));
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(e3, e3), w4.w));
+        int slot = kInitSlot;
+        double pen;
+        if (c < mK[b]) {
+          const TabEntry en = tab[(size_t)b * Kcap + c];
+          slot = en.slot;
+          atomicOr(reinterpret_cast<unsigned*>(lane_base(g) + L.l_used) + (slot >> 5), 1u << (slot & 31));
+          pen = (c == mLast[b]) ? p.log_1mp0 : (p.log_p0 + __ldg(p.logn + en.blocks)) - __ldg(p.logtot + mTot[b]);
+        } else {
+          pen = (p.log_p0 + p.log_alpha) - __ldg(p.logtot + mTot[b]);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          if (c < Kb) atomicOr(reinterpret_cast<unsigned*>(lane_base(g) + L.l_used) + (en.slot >> 5), 1u << (en.slot & 31));
-          float mse = acc;
-          if (d0sq == 0.f) mse = __fdiv_rn(acc, 0.f);  // zero "non-zero rows" (loss_func.py:36)
-          double pen;
-          if (c < Kb) pen = (c == mLast[b]) ? p.log_1mp0 : (p.log_p0 + p.logn[en.blocks]) - p.logtot[mTot[b]];
-          else pen = (p.log_p0 + p.log_alpha) - p.logtot[mTot[b]];
-          const float loss = __double2float_rn((double)mse - pen);
+        reinterpret_cast<double*>(lane_base(g) + L.l_keys)[e] = pen;
+        reinterpret_cast<unsigned*>(lane_base(g) + L.l_svals)[e] = (unsigned)slot | ((unsigned)b << 16) | ((unsigned)c << 21);
+      }
+      named_bar_sync(1, NT);
+      // P1b: one warp per candidate computes the 256-d weighted MSE against the slot's running
+      // mean.  Each warp takes kBatch candidates per trip and issues all their slot-pool loads
+      // (L2) before reducing any of them, so the L2 round trips overlap instead of serialising.
+      constexpr int kBatch = 4;
+      for (int f0 = warp * kBatch; f0 < ne_tot; f0 += NW * kBatch) {
+        int cg[kBatch], ce[kBatch];
+        unsigned cinfo[kBatch];
+        float4 m4[kBatch][(D + 127) / 128];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          const int f = f0 + q;
+          cg[q] = -1;
+          if (f < ne_tot) {
+            int g = 0, e = f;
+            while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
+            cg[q] = g; ce[q] = e;
+            cinfo[q] = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_svals)[e];
+            const float* mu = pool_mean_cta + g * pool_m_stride + (size_t)(cinfo[q] & 0xffffu) * D;
+#pragma unroll
+            for (int i = 0; i < (D + 127) / 128; ++i)
+              if (lane * 4 + i * 128 < D) m4[q][i] = *reinterpret_cast<const float4*>(mu + lane * 4 + i * 128);
+          }
+        }
+        // weighted_mse_loss for one row (loss_func.py:33-41): sum_d fl(fl(diff^2) * w_d)
+        float acc[kBatch], d0sq[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          acc[q] = 0.f; d0sq[q] = 1.f;
+          const int g = cg[q] < 0 ? 0 : cg[q];
+          const float* xs = reinterpret_cast<const float*>(lane_base(g) + L.l_xt) + (LSp(g)[LS_T] & 1) * D;
+#pragma unroll
+          for (int i = 0; i < (D + 127) / 128; ++i) {
+            const int d = lane * 4 + i * 128;
+            if (d < D && cg[q] >= 0) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xs + d);
+              const float4 w4 = *reinterpret_cast<const float4*>(wv + d);
+              const float e0 = __fsub_rn(m4[q][i].x, x4.x), e1 = __fsub_rn(m4[q][i].y, x4.y);
+              const float e2 = __fsub_rn(m4[q][i].z, x4.z), e3 = __fsub_rn(m4[q][i].w, x4.w);
+              const float q0 = __fmul_rn(e0, e0);
+              if (d == 0) d0sq[q] = q0;
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(q0, w4.x));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e1, e1), w4.y));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e2, e2), w4.z));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e3, e3), w4.w));
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // four interleaved butterfly reductions
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) acc[q] = __fadd_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o));
+        }
+        // lane q finishes candidate q (the four tails run side by side)
+        float my_acc = acc[0], my_d0 = __shfl_sync(0xffffffffu, d0sq[0], 0);
+        int my_g = cg[0], my_e = ce[0];
+        unsigned my_info = cinfo[0];
+#pragma unroll
+        for (int q = 1; q < kBatch; ++q) {
+          const float dq = __shfl_sync(0xffffffffu, d0sq[q], 0);
+          if (lane == q) { my_acc = acc[q]; my_d0 = dq; my_g = cg[q]; my_e = ce[q]; my_info = cinfo[q]; }
+        }
+        if (lane < kBatch && my_g >= 0) {
+          const int g = my_g, e = my_e;
+          volatile int* ls = LSp(g);
+          if (my_d0 == 0.f) my_acc = __fdiv_rn(my_acc, 0.f);  // zero "non-zero rows" (loss_func.py:36)
+          const int b = (int)((my_info >> 16) & 31u), c = (int)(my_info >> 21);
+          const float* mNl = reinterpret_cast<const float*>(lane_base(g) + L.l_meta) + ls[LS_GEN] * 4 * B + 3 * B;
+          const double pen = reinterpret_cast<const double*>(lane_base(g) + L.l_keys)[e];
+          // loss = fl32(f64(mse) - log terms); neg_likelihood accumulates in fp32 (uisrnn.py:452)
+          const float loss = __double2float_rn((double)my_acc - pen);
           const float S = __fadd_rn(mNl[b], loss);
           reinterpret_cast<float*>(lane_base(g) + L.l_svals)[e] = S;
           const unsigned flat = (unsigned)(b * (ls[LS_KMAX] + 1) + c);
@@ -605,6 +718,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
         }
       }
       named_bar_sync(1, NT);
+      UIS_PHASE(7);
 
       // ---- P2: rank by counting; the best min(#finite, B) become the new hypotheses (:546-552)
       for (int f = tid; f < ne_tot; f += NT) {
@@ -628,6 +742,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
         if (e == 0) ls[LS_NWIN] = nwin;
       }
       named_bar_sync(1, NT);
+      UIS_PHASE(8);
     }
 
     // ---- P3: warp g assigns lane g's GRU columns (distinct source slots) and allocates new
@@ -708,6 +823,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
       }
     }
     named_bar_sync(1, NT);
+    UIS_PHASE(9);
 
     // ---- P4: patch the one changed table entry per child; back-pointers; hypothesis meta;
     //          build the CTA-wide column list
@@ -904,7 +1020,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::NT + 32, 1) uis_beam_kernel(const B
     atomicAdd(&p.stats[2], st_cand);
     atomicAdd(&p.stats[3], st_steps);
     atomicMax(&p.stats[4], (unsigned long long)st_maxk);
-    for (int i = 0; i < 6; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
+    for (int i = 0; i < 10; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }
 }
 

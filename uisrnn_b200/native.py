@@ -42,7 +42,7 @@ class Stats(C.Structure):
   _fields_ = [('utterances', C.c_int64), ('frames', C.c_int64), ('beam_steps', C.c_int64),
               ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
               ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32),
-              ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('reserved', C.c_int32), ('phase_cycles', C.c_int64 * 6)]
+              ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('reserved', C.c_int32), ('phase_cycles', C.c_int64 * 10)]
 
   def as_dict(self):
     out = {}
