@@ -35,7 +35,8 @@ typedef enum uis_status {
   UIS_ERR_UNSUPPORTED = -2, /* shape / option the sm_100a kernels are not instantiated for     */
   UIS_ERR_CUDA = -3,        /* a CUDA runtime call failed; uis_last_error() has the string     */
   UIS_ERR_OVERFLOW = -4,    /* a hypothesis opened more than `kcap` clusters; retry with more  */
-  UIS_ERR_NOMEM = -5
+  UIS_ERR_NOMEM = -5,
+  UIS_ERR_CAPACITY = -6     /* look_ahead >= 2: a beam step's candidate tree outgrew on-chip storage */
 } uis_status;
 
 typedef struct uis_model uis_model; /* opaque */
@@ -45,7 +46,8 @@ typedef struct uis_predict_opts {
   int32_t beam_size;      /* --beam_size      (arguments.py:175-180), >= 1                     */
   int32_t look_ahead;     /* --look_ahead     (arguments.py:181-185), >= 1                     */
   int32_t test_iteration; /* --test_iteration (arguments.py:186-193), >= 1                     */
-  int32_t kcap;           /* max clusters per hypothesis held on device; 0 = default (32)      */
+  int32_t kcap;           /* max clusters per hypothesis held on device; 0 = default (32; 16
+                             when look_ahead >= 2)                                             */
   int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
   int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
                              0 = auto (2 when U >= 2 * CTAs, else 1), max 4                    */

@@ -60,8 +60,8 @@ def compare_trace(win, score, off, gwin, gscore, goff, rtol=1e-5):
   swaps = 0
   for s in range(len(off) - 1):
     lo, hi = int(off[s]), int(off[s + 1])
-    a = [prev_a[int(win[r, 0])] + (int(win[r, 1]),) for r in range(lo, hi)]
-    b = [prev_b[int(gwin[r, 0])] + (int(gwin[r, 1]),) for r in range(lo, hi)]
+    a = [prev_a[int(win[r, 0])] + tuple(int(v) for v in win[r, 1:] if v >= 0) for r in range(lo, hi)]
+    b = [prev_b[int(gwin[r, 0])] + tuple(int(v) for v in gwin[r, 1:] if v >= 0) for r in range(lo, hi)]
     if a != b:
       sb = {h: float(v) for h, v in zip(b, gscore[lo:hi])}
       cutoff = float(gscore[hi - 1])

@@ -55,8 +55,9 @@ def test_unsupported_configurations_raise_instead_of_falling_back():
   from uisrnn_b200 import native
   small = uisrnn_from_weights(load_weights('model_small.npz'), enable_cuda=True)
   case = [c for c in small_cases() if c['name'] == 'la2'][0]
+  assert small.predict(case['x'], inference_args(5, 2, 1)) == case['labels'].tolist()   # look_ahead 2 kernel
   with pytest.raises(native.NativeError) as ei:
-    small.predict(case['x'], inference_args(5, 2, 1))            # look_ahead 2: no kernel yet
+    small.predict(case['x'], inference_args(40, 1, 1))           # beam > 32: no kernel
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   import uisrnn
   m, _, _ = uisrnn.parse_arguments([])

@@ -39,10 +39,10 @@ def test_model_constants_match_oracle(small_model, toy_model):
     assert np.max(np.abs(hidden0 - om.hidden0[0])) < STATE_ATOL
 
 
-@pytest.mark.parametrize('case', [c for c in small_cases() if c['look_ahead'] == 1],
-                         ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', small_cases(), ids=lambda c: c['name'])
 def test_small_cases_match_reference_golden(small_model, case):
-  labs, dbg = small_model.predict([case['x']], beam_size=case['beam_size'], look_ahead=1,
+  """Beam sizes 1/3/10/30, look_ahead 1/2/3 (incl. a shorter tail chunk), test_iteration 1/2/3."""
+  labs, dbg = small_model.predict([case['x']], beam_size=case['beam_size'], look_ahead=case['look_ahead'],
                                   test_iteration=case['test_iteration'], trace_utt=0)
   assert labs[0].tolist() == case['labels'].tolist()
   swaps = compare_trace(dbg['win'], dbg['score'], dbg['off'], case['win'], case['score'], case['off'],
@@ -139,7 +139,31 @@ def test_kcap_overflow_fails_loudly(small_model, native):
 def test_unsupported_options_fail_loudly(small_model, native):
   x = np.zeros((4, 64))
   with pytest.raises(native.NativeError) as ei:
-    small_model.predict([x], look_ahead=2)
+    small_model.predict([x], look_ahead=9)
+  assert ei.value.code == native.UIS_ERR_UNSUPPORTED
+  with pytest.raises(native.NativeError) as ei:
+    small_model.predict([x], beam_size=33)
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   with pytest.raises(native.NativeError):
     small_model.predict([x], beam_size=0)
+
+
+@pytest.mark.parametrize('beam,la,titer', [(10, 2, 2), (6, 3, 1), (30, 2, 1), (3, 4, 1)])
+def test_look_ahead_fresh_inputs_match_oracle(small_model, beam, la, titer):
+  from uisrnn_b200.synth import synth_utt
+  om = oracle_model('model_small.npz')
+  xs = [synth_utt(9500 + i, n_frames=n, dim=64, n_spk=k, noise=0.08)[0]
+        for i, (n, k) in enumerate([(31, 3), (1, 1), (24, 2), (3, 2)])]
+  got = small_model.predict(xs, beam_size=beam, look_ahead=la, test_iteration=titer)
+  for x, o in zip(xs, got):
+    want = uis_oracle.predict_single(om, x, beam_size=beam, look_ahead=la, test_iteration=titer)
+    assert o.tolist() == want
+
+
+def test_wide_beam_look_ahead_config3_shape(toy_model):
+  """BASELINE config 3 (beam_size=30, look_ahead=2, hidden=512) on a short utterance vs the oracle."""
+  from uisrnn_b200.synth import synth_utt
+  om = oracle_model('model_toy100.npz')
+  x = synth_utt(1234, n_frames=24)[0]
+  got = toy_model.predict([x], beam_size=30, look_ahead=2, test_iteration=2)[0]
+  assert got.tolist() == uis_oracle.predict_single(om, x, beam_size=30, look_ahead=2, test_iteration=2)

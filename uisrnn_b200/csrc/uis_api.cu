@@ -16,6 +16,7 @@
 
 #include "../../include/uisrnn_b200.h"
 #include "uis_beam.cuh"
+#include "uis_beam_tree.cuh"
 #include "uis_prepass.cuh"
 
 namespace {
@@ -111,6 +112,33 @@ unsigned smem_bytes(int H, int D, int B, int Kcap, int G) {
   return 0xffffffffu;
 }
 
+template <int H, int D>
+int launch_tree(const uis::BeamParams& p, int ctas, cudaStream_t st) {
+  const uis::TreeLayout T = uis::make_tree_layout<H, D>(p.B, p.Kcap, p.L, p.node_cap, p.leaf_cap, p.P);
+  if (T.total > 227 * 1024)
+    return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d beam_size=%d kcap=%d needs %u B of shared memory (> 227 KB)", p.L,
+                p.B, p.Kcap, T.total);
+  auto kern = uis::uis_beam_tree_kernel<H, D>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total));
+  kern<<<ctas, uis::Cfg<H, D>::BLOCK, T.total, st>>>(p);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+unsigned tree_smem_bytes(int H, int D, int B, int Kcap, int L, int NI, int NLF, int P) {
+  if (H == 512 && D == 256) return uis::make_tree_layout<512, 256>(B, Kcap, L, NI, NLF, P).total;
+  if (H == 256 && D == 128) return uis::make_tree_layout<256, 128>(B, Kcap, L, NI, NLF, P).total;
+  if (H == 128 && D == 64) return uis::make_tree_layout<128, 64>(B, Kcap, L, NI, NLF, P).total;
+  return 0xffffffffu;
+}
+
+int dispatch_tree(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t st) {
+  if (H == 512 && D == 256) return launch_tree<512, 256>(p, ctas, st);
+  if (H == 256 && D == 128) return launch_tree<256, 128>(p, ctas, st);
+  if (H == 128 && D == 64) return launch_tree<128, 64>(p, ctas, st);
+  return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+}
+
 bool shape_supported(int H, int D) {
   return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64);
 }
@@ -157,6 +185,7 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 
 struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
+  int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
   long long rows;
 };
 
@@ -165,14 +194,15 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   if (U < 0) return fail(UIS_ERR_INVALID, "U < 0");
   if (o->beam_size < 1 || o->look_ahead < 1 || o->test_iteration < 1)
     return fail(UIS_ERR_INVALID, "beam_size, look_ahead and test_iteration must be >= 1");
-  if (o->look_ahead != 1)
-    return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d: the sm_100a kernel implements look_ahead=1 only", o->look_ahead);
+  if (o->look_ahead > 8) return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d > 8 not supported", o->look_ahead);
   if (o->beam_size > 32) return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > 32 not supported", o->beam_size);
   pl->B = o->beam_size;
   pl->L = o->look_ahead;
   pl->T = o->test_iteration;
-  pl->Kcap = o->kcap > 0 ? o->kcap : 32;
+  const bool tree = pl->L > 1;
+  pl->Kcap = o->kcap > 0 ? o->kcap : (tree ? 16 : 32);
   if (pl->Kcap > 2047 || pl->B * pl->Kcap + pl->B + 1 > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
+  if (tree && pl->Kcap > 255) return fail(UIS_ERR_UNSUPPORTED, "look_ahead >= 2 supports kcap <= 255");
   pl->P = pl->B * pl->Kcap + pl->B + 1;
   pl->rows = U > 0 ? off[U] : 0;
   int maxN = 0;
@@ -187,7 +217,27 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   // lanes (utterances advanced together by one CTA, sharing each weight pass): 2 when there is
   // enough work to keep every CTA's lanes busy, else 1 (latency mode); opts->lanes overrides.
   int G = o->lanes > 0 ? std::min(o->lanes, (int)uis::kMaxLanes) : ((long long)U >= 2ll * ctas ? 2 : 1);
-  while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
+  if (tree) {
+    // look-ahead tree kernel: one utterance per CTA; size the on-chip node / leaf arrays to what
+    // shared memory allows (internal nodes : leaves ~ 1 : 8, the typical fan-out K+2)
+    G = 1;
+    long long tn = 0;
+    for (int u = 0; u < U; ++u) tn = std::max<long long>(tn, (off[u + 1] - off[u]) * pl->T);
+    pl->maxTN = (int)std::max<long long>(tn, 1);
+    pl->maxSteps = (pl->maxTN + pl->L - 1) / pl->L;
+    int ni = 64;
+    auto fits = [&](int n) {
+      const int P = pl->B * pl->Kcap + n + pl->B + 1;
+      return tree_smem_bytes(m->H, m->D, pl->B, pl->Kcap, pl->L, n, 8 * n, P) <= 227u * 1024u;
+    };
+    if (!fits(ni)) return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d beam_size=%d kcap=%d does not fit in shared memory", pl->L, pl->B, pl->Kcap);
+    while (ni < 4096 && fits(ni + 32)) ni += 32;
+    pl->node_cap = ni;
+    pl->leaf_cap = 8 * ni;
+    pl->P = pl->B * pl->Kcap + ni + pl->B + 1;
+  } else {
+    while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
+  }
   pl->G = G;
   pl->ctas = std::max(1, std::min(ctas, std::max((U + G - 1) / G, 1)));
   return 0;
@@ -197,7 +247,7 @@ size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
   size_t b = 0;
   b += (size_t)pl.rows * 3 * m->H * 4;                                  // gi
   b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->H) * 4;               // slot pools
-  b += (size_t)pl.ctas * pl.G * pl.maxN * pl.B * 4;                     // back-pointers
+  b += (size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B * 4;  // back-pointers
   b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
   return b;
 }
@@ -234,7 +284,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
   if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.G * pl.P * D * sizeof(float))) return rc;
   if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * H * sizeof(float))) return rc;
-  if (int rc = m->bp.ensure((size_t)pl.ctas * pl.G * pl.maxN * pl.B * sizeof(unsigned))) return rc;
+  if (int rc = m->bp.ensure((size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B *
+                            sizeof(unsigned)))
+    return rc;
 
   CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -252,6 +304,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.x = x_dev; p.gi = m->gi.as<float>();
   p.row_off = m->row_off.as<long long>(); p.order = m->order.as<int>();
   p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN; p.G = pl.G;
+  p.L = pl.L; p.node_cap = pl.node_cap; p.leaf_cap = pl.leaf_cap; p.maxTN = pl.maxTN; p.maxSteps = pl.maxSteps;
   { const char* e = getenv("UIS_DBG_MODE"); p.dbg_mode = e ? atoi(e) : 0; }
   p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>();
   p.bp = m->bp.as<unsigned>();
@@ -271,9 +324,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
     if (taps->trace_utt >= 0 && taps->trace_utt < U) {
       p.trace_utt = taps->trace_utt;
       p.trace_capacity = std::max(taps->trace_capacity, 0);
-      trace_steps = (off[p.trace_utt + 1] - off[p.trace_utt]) * pl.T;
+      trace_steps = ((off[p.trace_utt + 1] - off[p.trace_utt]) * pl.T + pl.L - 1) / pl.L;
       if (taps->step_winners && p.trace_capacity > 0) {
-        if (int rc = m->dbg_win.ensure((size_t)p.trace_capacity * 8)) return rc;
+        if (int rc = m->dbg_win.ensure((size_t)p.trace_capacity * 4 * (1 + pl.L))) return rc;
         if (int rc = m->dbg_score.ensure((size_t)p.trace_capacity * 4)) return rc;
         if (int rc = m->dbg_off.ensure((size_t)(trace_steps + 1) * 8)) return rc;
         p.dbg_win = m->dbg_win.as<int>(); p.dbg_score = m->dbg_score.as<float>();
@@ -301,7 +354,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   }
   CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
-  if (int rc = dispatch_beam(H, D, p, pl.ctas, st)) return rc;
+  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st) : dispatch_beam(H, D, p, pl.ctas, st))) return rc;
   CU(cudaEventRecord(m->ev[2], st));
   m->stats.kernel_launches = 2;
   m->stats_pending = true;
@@ -313,7 +366,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
       if (taps->final_k) CU(cudaMemcpy(taps->final_k, p.dbg_final_k, (size_t)U * 4, cudaMemcpyDeviceToHost));
     }
     if (p.dbg_win) {
-      CU(cudaMemcpy(taps->step_winners, p.dbg_win, (size_t)p.trace_capacity * 8, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(taps->step_winners, p.dbg_win, (size_t)p.trace_capacity * 4 * (1 + pl.L), cudaMemcpyDeviceToHost));
       CU(cudaMemcpy(taps->step_scores, p.dbg_score, (size_t)p.trace_capacity * 4, cudaMemcpyDeviceToHost));
       if (taps->step_offsets)
         CU(cudaMemcpy(taps->step_offsets, p.dbg_off, (size_t)(trace_steps + 1) * 8, cudaMemcpyDeviceToHost));
@@ -346,11 +399,15 @@ int collect(uis_model* m) {
   m->stats_pending = false;
   std::vector<int> status(m->last_U);
   CU(cudaMemcpy(status.data(), m->status.p, (size_t)m->last_U * sizeof(int), cudaMemcpyDeviceToHost));
-  int overflow = 0, bad = 0;
+  int overflow = 0, bad = 0, capacity = 0;
   for (int v : status) {
     if (v == -4) ++overflow;
+    else if (v == -5) ++capacity;
     else if (v != 0) ++bad;
   }
+  if (capacity)
+    return fail(UIS_ERR_CAPACITY, "%d utterance(s): the look-ahead tree of one beam step outgrew the on-chip node arrays "
+                "(lower beam_size / look_ahead / kcap)", capacity);
   if (overflow)
     return fail(UIS_ERR_OVERFLOW, "%d utterance(s) opened more clusters than kcap; retry with a larger kcap", overflow);
   if (bad) return fail(UIS_ERR_INVALID, "%d utterance(s) ended with no finite hypothesis", bad);

@@ -66,6 +66,7 @@ struct BeamParams {
   const long long* row_off; // [U + 1]
   const int* order;         // [U] utterance ids, longest first
   int U, B, Kcap, T, P, maxN, G;
+  int L, node_cap, leaf_cap, maxTN, maxSteps;  // look_ahead >= 2 (uis_beam_tree.cuh) only
   int dbg_mode;  // 0 normal; 1 = stream the weights but skip the math (timing experiment, results invalid)
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
@@ -352,11 +353,12 @@ struct ColCtx {
   const int* src;   // source slot
   const int* dst;   // new slot
   const int* vis;   // visits of the source entry BEFORE this update
-  const int* gi;    // float offset (from smem base) of the lane's current gi row
+  const int* gi;    // float offset (from smem base) of the lane's current gi row   (GIG == false)
+  const long long* girow;  // row of p.gi holding W_ih x + b_ih for the column's frame (GIG == true)
 };
 
 // ---- one full weight pass (GRU -> W1 -> W2) for columns [m0, m0 + Mp) -----------------------
-template <class C, int NC>
+template <class C, int NC, bool GIG = false>
 __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
                                          unsigned& it, float* XA, float* XB, const float* smem_f,
                                          const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
@@ -382,7 +384,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
           const int m = 4 * c + q;
           hn[q] = 0.f;
           if (m < Mp) {
-            const float* gi = smem_f + cc.gi[m0 + m];
+            const float* gi = GIG ? p.gi + (size_t)cc.girow[m0 + m] * 3 * H : smem_f + cc.gi[m0 + m];
             const float r = sigmoid_f32(__fadd_rn(gi[j], __fadd_rn(acc[0 * UPT + u][m], bh[0 * UPT + u])));
             const float z = sigmoid_f32(__fadd_rn(gi[H + j], __fadd_rn(acc[1 * UPT + u][m], bh[1 * UPT + u])));
             const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(r, __fadd_rn(acc[2 * UPT + u][m], bh[2 * UPT + u]))));
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
 
   int* collane = colarr; int* colsrc = colarr + G * B; int* colnew = colarr + 2 * G * B;
   int* colvis = colarr + 3 * G * B; int* colgi = colarr + 4 * G * B;
-  const ColCtx cc{collane, colsrc, colnew, colvis, colgi};
+  const ColCtx cc{collane, colsrc, colnew, colvis, colgi, nullptr};
 
   unsigned it = 0;  // weight-ring tile counter (identical in every consumer thread)
   unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;

@@ -86,6 +86,11 @@ __device__ __forceinline__ uint32_t float_order_key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// inverse of float_order_key (for non-NaN keys)
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __device__ __forceinline__ float sigmoid_f32(float v) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
 }

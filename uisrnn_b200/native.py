@@ -17,6 +17,7 @@ UIS_ERR_UNSUPPORTED = -2
 UIS_ERR_CUDA = -3
 UIS_ERR_OVERFLOW = -4
 UIS_ERR_NOMEM = -5
+UIS_ERR_CAPACITY = -6
 
 
 class NativeError(RuntimeError):
@@ -158,8 +159,8 @@ class NativeModel:
 
   def _taps(self, trace_utt, n_utt, lengths, beam_size, look_ahead, test_iteration, kcap):
     """Allocates host buffers for the debug taps; returns (struct, dict of arrays)."""
-    kcap = kcap or 32
-    steps = int(lengths[trace_utt]) * test_iteration if trace_utt >= 0 else 0
+    kcap = kcap or (32 if look_ahead == 1 else 16)
+    steps = -(-int(lengths[trace_utt]) * test_iteration // look_ahead) if trace_utt >= 0 else 0
     cap = max(1, steps * beam_size)
     bufs = {
         'win': np.full((cap, 1 + look_ahead), -1, np.int32),
