@@ -145,6 +145,41 @@ size_t uis_predict_workspace_bytes(uis_model* m, const int64_t* frame_offsets, i
 
 int uis_get_stats(uis_model* m, uis_stats* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training: one iteration of UISRNN.fit_concatenated (uisrnn/uisrnn.py:252-295) on the device.
+ * Parameters are the ten tensors below, in this order, row-major fp32 (PyTorch layouts):
+ *   0 gru.weight_ih_l0 [3H,D]  1 gru.weight_hh_l0 [3H,H]  2 gru.bias_ih_l0 [3H]  3 gru.bias_hh_l0 [3H]
+ *   4 linear_mean1.weight [H,H] 5 linear_mean1.bias [H]   6 linear_mean2.weight [D,H] 7 linear_mean2.bias [D]
+ *   8 rnn_init_hidden [H]       9 sigma2 [D]
+ * (0-7 = the "rnn parameters" group that is norm-clipped, uisrnn.py:120-133, 292.)
+ */
+typedef struct uis_trainer uis_trainer; /* opaque; owns parameters, gradients and Adam state */
+
+typedef struct uis_train_hparams {          /* training_args, uisrnn/arguments.py:105-169 */
+  float learning_rate;                      /* --learning_rate                                   */
+  float sigma_alpha, sigma_beta;            /* --sigma_alpha / --sigma_beta                      */
+  float regularization_weight;              /* --regularization_weight                           */
+  float grad_max_norm;                      /* --grad_max_norm                                   */
+  int32_t train_sigma2;                     /* 1 if sigma2 is estimated (model_args.sigma2 None) */
+} uis_train_hparams;
+
+/* params: ten host (or device) pointers, copied.  Adam state starts at zero (a fresh optimiser per
+ * fit_concatenated call, uisrnn.py:235-236). */
+int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float* const* params,
+                       const uis_train_hparams* hp);
+int uis_trainer_destroy(uis_trainer* t);
+
+/* One iteration on one batch = what utils.pack_sequence builds (utils.py:237-246): x_host fp32
+ * [L][B][D] zero-padded, time-major, row 0 all zeros; lengths[B] (incl. the zero row) sorted
+ * descending with lengths[0] == L; B <= 32.  mode 0: forward + backward + clip + Adam + clamp;
+ * mode 1: forward + backward only (for gradient checks).  losses_out[3] (host, may be NULL) =
+ * negative log likelihood, sigma2 prior, regularisation -- the three numbers uisrnn.py:297-310 logs. */
+int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
+                     float* losses_out, void* stream);
+
+/* what = 0: current parameters, 1: gradients of the last step.  out: ten host pointers (NULL = skip). */
+int uis_trainer_get(uis_trainer* t, int what, float* const* out);
+
 #ifdef __cplusplus
 }
 #endif

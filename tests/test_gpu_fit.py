@@ -1,0 +1,160 @@
+"""fit() on the device (csrc/uis_train.cu through the C ABI) against PyTorch autograd on the same
+batch: the three loss terms, every gradient, one Adam step, and a short training trajectory."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _model_and_data(D=64, H=128, seed=11):
+  import torch
+  import uisrnn
+  from uisrnn_b200.synth import synth_training_set
+  # the autograd reference must be true fp32: cuDNN's RNN uses TF32 tensor cores by default
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  np.random.seed(seed); random.seed(seed); torch.manual_seed(seed)
+  m, t, _ = uisrnn.parse_arguments([])
+  m.observation_dim, m.rnn_hidden_size, m.verbosity = D, H, 0
+  t.batch_size, t.learning_rate, t.train_iteration = 12, 1e-3, 1
+  model = uisrnn.UISRNN(m)
+  assert model.device.type == 'cuda'
+  with torch.no_grad():
+    model.rnn_init_hidden.data.normal_(0, 0.1)
+    model.sigma2.data.uniform_(0.05, 0.2)
+  seqs, ids = synth_training_set(4000, 30, n_frames=50, dim=D, n_spk=3, noise=0.08)
+  from uisrnn_b200 import utils
+  x, y = utils.concatenate_training_data(seqs, ids, True, True)
+  subs, lens = utils.resize_sequence(x, np.array(y), t.num_permutations)
+  return model, t, subs, lens
+
+
+def _torch_losses_and_grads(model, targs, rnn_input, lengths):
+  import torch
+  from torch import nn
+  from uisrnn_b200 import loss_func
+  dev = model.device
+  x = torch.from_numpy(rnn_input).float().to(dev)
+  packed = nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=False)
+  truth = x[1:]
+  for p in list(model.rnn_model.parameters()) + [model.rnn_init_hidden, model.sigma2]:
+    p.grad = None
+  mean, _ = model.rnn_model(packed, model.rnn_init_hidden.repeat(1, x.size(1), 1))
+  steps = torch.arange(1, mean.size(0) + 1, device=dev).float()
+  mean = torch.cumsum(mean, dim=0) * (1.0 / steps).view(-1, 1, 1)
+  mask = (truth != 0).float()
+  loss1 = loss_func.weighted_mse_loss(mask * mean[:-1], truth, 1 / (2 * model.sigma2))
+  res = ((mask * mean[:-1] - truth) ** 2).view(-1, x.size(2))
+  nnz = torch.sum((res != 0).float(), dim=0).squeeze()
+  loss2 = loss_func.sigma2_prior_loss(nnz, targs.sigma_alpha, targs.sigma_beta, model.sigma2)
+  loss3 = loss_func.regularization_loss(model.rnn_model.parameters(), targs.regularization_weight)
+  (loss1 + loss2 + loss3).backward()
+  grads = {n: p.grad.detach().cpu().numpy() for n, p in model.rnn_model.named_parameters()}
+  grads['rnn_init_hidden'] = model.rnn_init_hidden.grad.detach().cpu().numpy().reshape(-1)
+  grads['sigma2'] = model.sigma2.grad.detach().cpu().numpy()
+  return (float(loss1), float(loss2), float(loss3)), grads
+
+
+def _native_trainer(model, targs):
+  from uisrnn_b200 import native
+  state = {k: v.detach().cpu().numpy() for k, v in model.rnn_model.state_dict().items()}
+  params = {k: state[k] for k in native.PARAM_ORDER[:8]}
+  params['rnn_init_hidden'] = model.rnn_init_hidden.detach().cpu().numpy().reshape(-1)
+  params['sigma2'] = model.sigma2.detach().cpu().numpy()
+  hp = {'learning_rate': targs.learning_rate, 'sigma_alpha': targs.sigma_alpha, 'sigma_beta': targs.sigma_beta,
+        'regularization_weight': targs.regularization_weight, 'grad_max_norm': targs.grad_max_norm,
+        'train_sigma2': True}
+  return native.NativeTrainer(params, hp)
+
+
+def _rel(a, b):
+  return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-20))
+
+
+def test_losses_and_gradients_match_autograd():
+  from uisrnn_b200 import utils
+  model, targs, subs, lens = _model_and_data()
+  model.rnn_model.train()
+  rnn_input, lengths = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+  want_losses, want = _torch_losses_and_grads(model, targs, rnn_input, lengths)
+  trainer = _native_trainer(model, targs)
+  got_losses = trainer.step(rnn_input.astype(np.float32), lengths, grads_only=True)
+  got = trainer.gradients()
+  for a, b in zip(got_losses, want_losses):
+    assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (got_losses, want_losses)
+  for name in want:
+    assert _rel(got[name].reshape(want[name].shape), want[name]) < 2e-3, name
+
+
+def test_one_adam_step_matches_torch():
+  import torch
+  from torch import nn
+  from uisrnn_b200 import utils
+  model, targs, subs, lens = _model_and_data(seed=12)
+  model.rnn_model.train()
+  rnn_input, lengths = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+  trainer = _native_trainer(model, targs)
+  trainer.step(rnn_input.astype(np.float32), lengths)
+  got = trainer.parameters()
+  optimizer = model._get_optimizer('adam', targs.learning_rate)   # pylint: disable=protected-access
+  optimizer.zero_grad()
+  _torch_losses_and_grads(model, targs, rnn_input, lengths)
+  nn.utils.clip_grad_norm_(model.rnn_model.parameters(), targs.grad_max_norm)
+  optimizer.step()
+  model.sigma2.data.clamp_(min=1e-6)
+  for name, p in model.rnn_model.named_parameters():
+    assert np.max(np.abs(got[name] - p.detach().cpu().numpy())) < 2e-5, name   # lr = 1e-3: |update| <= 1e-3
+  assert np.max(np.abs(got['sigma2'] - model.sigma2.detach().cpu().numpy())) < 2e-5
+  assert np.max(np.abs(got['rnn_init_hidden'] - model.rnn_init_hidden.detach().cpu().numpy().reshape(-1))) < 2e-5
+
+
+def test_training_trajectory_matches_torch_path(monkeypatch):
+  """20 iterations with the same RNG stream: native loss1 trajectory within 1e-3 of the autograd path
+  (SURVEY.md section 8(d), config 4 criterion)."""
+  import torch
+  from uisrnn_b200 import utils
+
+  def run(native_path):
+    model, targs, subs, lens = _model_and_data(seed=13)
+    np.random.seed(99)
+    losses = []
+    if native_path:
+      trainer = _native_trainer(model, targs)
+      for _ in range(20):
+        x, l = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+        losses.append(trainer.step(x.astype(np.float32), l)[0])
+    else:
+      model.rnn_model.train()
+      opt = model._get_optimizer('adam', targs.learning_rate)   # pylint: disable=protected-access
+      for _ in range(20):
+        x, l = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+        opt.zero_grad()
+        (l1, _, _), _ = _torch_losses_and_grads(model, targs, x, l)
+        torch.nn.utils.clip_grad_norm_(model.rnn_model.parameters(), targs.grad_max_norm)
+        opt.step()
+        model.sigma2.data.clamp_(min=1e-6)
+        losses.append(l1)
+    return np.array(losses)
+
+  a, b = run(True), run(False)
+  assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < 1e-3, (a, b)
+
+
+def test_fit_api_uses_native_trainer_and_learns():
+  import torch
+  import uisrnn
+  from uisrnn_b200.synth import synth_training_set, synth_utt
+  np.random.seed(5); random.seed(5); torch.manual_seed(5)
+  m, t, i = uisrnn.parse_arguments([])
+  m.observation_dim, m.rnn_hidden_size, m.verbosity = 64, 128, 0
+  t.batch_size, t.learning_rate, t.train_iteration = 16, 2e-3, 150
+  model = uisrnn.UISRNN(m)
+  seqs, ids = synth_training_set(6000, 60, n_frames=60, dim=64, n_spk=3, noise=0.08)
+  model.fit(seqs, ids, t)
+  losses = model.last_training_losses
+  assert len(losses) == 150 and np.all(np.isfinite(losses))   # likelihood term only, as uisrnn.py:311
+  x, truth = synth_utt(6100, n_frames=80, dim=64, n_spk=3, noise=0.08)
+  acc = uisrnn.compute_sequence_match_accuracy(model.predict(x, i), truth.tolist())
+  assert acc > 0.9

@@ -20,10 +20,12 @@
 #include "uis_prepass.cuh"
 
 namespace {
-
 thread_local std::string g_err;
+}
 
-int fail(int code, const char* fmt, ...) {
+namespace uis {
+// shared with uis_train.cu
+int api_fail(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -31,6 +33,14 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   g_err = buf;
   return code;
+}
+}  // namespace uis
+
+namespace {
+
+template <class... Args>
+int fail(int code, const char* fmt, Args... args) {
+  return uis::api_fail(code, fmt, args...);
 }
 
 #define CU(call)                                                                              \

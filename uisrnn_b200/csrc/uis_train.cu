@@ -1,0 +1,533 @@
+// fit() on the device: one training iteration of UISRNN.fit_concatenated
+// (/root/reference/uisrnn/uisrnn.py:252-295) as hand-written sm_100a kernels behind a C ABI:
+//   packed-sequence GRU forward (:262-263 -> CoreRNN.forward :45-52), MLP, running mean over time
+//   (:265-271), masked weighted-MSE likelihood (:274-277, loss_func.py:19-41), sigma^2 prior
+//   (:280-284, loss_func.py:44-60), parameter-norm regulariser (:287-288, loss_func.py:63-76),
+//   full backward pass (what autograd does at :290), gradient-norm clipping of the RNN parameters
+//   (:292), Adam step (:293, torch.optim.Adam defaults) and the sigma^2 clamp (:295).
+// Layout: time-major zero-padded batch X[L][B][D] with per-sequence lengths sorted descending
+// (exactly what utils.pack_sequence builds before pack_padded_sequence, utils.py:237-246); at time
+// t the first batch_t = #{len_b > t} sequences are live, as in a PackedSequence.
+// All arithmetic fp32.  The derivation of the backward pass is checked against torch autograd in
+// tools/fit_manual_check.py (CPU) and tests/test_gpu_fit.py (device).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/uisrnn_b200.h"
+#include "uis_common.cuh"
+
+namespace uis {
+int api_fail(int code, const char* fmt, ...);  // defined in uis_api.cu (sets uis_last_error)
+}
+
+#define CUT(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return uis::api_fail(UIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace uis {
+
+// ---------------------------------------------------------------------------------------------
+// Generic fp32 GEMM:  C[M][N] (+)= opA(A)[M][K] * opB(B)[K][N]  (+ bias[N]) (relu) (* (mask > 0))
+//   TA == false: A stored [M][K];  TA == true: A stored [K][M]
+//   TB == false: B stored [K][N];  TB == true: B stored [N][K]   (PyTorch Linear weight layout)
+// 64x64 CTA tile, BK = 16, 256 threads, 4x4 register micro-tile, k ascending per thread.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                   const float* __restrict__ bias, const float* __restrict__ mask,
+                                                   float* __restrict__ C, int M, int N, int K, int relu,
+                                                   int accumulate) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int q = tid; q < 64 * 16; q += 256) {
+      int mm, kk;
+      if (TA) { mm = q % 64; kk = q / 64; } else { kk = q % 16; mm = q / 16; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      As[kk][mm] = v;
+    }
+    for (int q = tid; q < 64 * 16; q += 256) {
+      int nn, kk;
+      if (TB) { kk = q % 16; nn = q / 16; } else { nn = q % 64; kk = q / 64; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < K) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask) v = (mask[(size_t)gm * N + gn] > 0.f) ? v : 0.f;
+      if (accumulate) v += C[(size_t)gm * N + gn];
+      C[(size_t)gm * N + gn] = v;
+    }
+  }
+}
+
+// column sums: out[n] = sum_r A[r][n]   (one warp per 32 columns, rows strided over the block)
+__global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ out, int R, int N) {
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N)
+    for (int r = w; r < R; r += 8) s += A[(size_t)r * N + n];
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+    for (int q = 0; q < 8; ++q) t += part[q][lane];
+    out[n] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRU forward, one time step: for b < nb, j < H
+//   gh = W_hh h_{t-1} + b_hh ; r,z = sigmoid(gi + gh) ; n = tanh(gi_n + r * gh_n) ; h = (h_prev - n) z + n
+// Block = (8 hidden units) x (32 sequences); h_prev staged transposed in shared memory.
+__global__ void __launch_bounds__(256) gru_fwd_step_kernel(const float* __restrict__ whh, const float* __restrict__ bhh,
+                                                           const float* __restrict__ gi_t, const float* __restrict__ hprev,
+                                                           float* __restrict__ hnew, float* __restrict__ r_t,
+                                                           float* __restrict__ z_t, float* __restrict__ n_t,
+                                                           float* __restrict__ hn_t, int B, int nb, int H) {
+  extern __shared__ float hs[];  // [H][33]
+  const int tid = threadIdx.x;
+  for (int q = tid; q < nb * H; q += 256) {
+    const int b = q / H, k = q % H;
+    hs[k * 33 + b] = hprev[(size_t)b * H + k];
+  }
+  __syncthreads();
+  const int b = tid % 32, j = blockIdx.x * 8 + tid / 32;
+  if (b >= nb || j >= H) return;
+  const float* wr = whh + (size_t)j * H;
+  const float* wz = whh + (size_t)(H + j) * H;
+  const float* wn = whh + (size_t)(2 * H + j) * H;
+  float ar = 0.f, az = 0.f, an = 0.f;
+  for (int k = 0; k < H; ++k) {
+    const float h = hs[k * 33 + b];
+    ar = fmaf(wr[k], h, ar); az = fmaf(wz[k], h, az); an = fmaf(wn[k], h, an);
+  }
+  const float* gi = gi_t + (size_t)b * 3 * H;
+  const float r = sigmoid_f32(gi[j] + (ar + bhh[j]));
+  const float z = sigmoid_f32(gi[H + j] + (az + bhh[H + j]));
+  const float hn = an + bhh[2 * H + j];
+  const float n = tanhf(gi[2 * H + j] + r * hn);
+  const float hp = hs[j * 33 + b];
+  const size_t o = (size_t)b * H + j;
+  hnew[o] = (hp - n) * z + n;
+  r_t[o] = r; z_t[o] = z; n_t[o] = n; hn_t[o] = hn;
+}
+
+// GRU backward, elementwise part of one time step (b < nb):
+//   dh = dout_t + carry ; gate gradients ; dGi_t, dGh_t ; carry <- dh * z   (the W_hh^T dGh term is a GEMM)
+__global__ void gru_bwd_step_kernel(const float* __restrict__ dout_t, float* __restrict__ carry,
+                                    const float* __restrict__ r_t, const float* __restrict__ z_t,
+                                    const float* __restrict__ n_t, const float* __restrict__ hn_t,
+                                    const float* __restrict__ hprev, float* __restrict__ dgi_t,
+                                    float* __restrict__ dgh_t, int nb, int H) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb * H) return;
+  const int b = q / H, j = q % H;
+  const float dh = dout_t[q] + carry[q];
+  const float r = r_t[q], z = z_t[q], n = n_t[q], hn = hn_t[q], hp = hprev[q];
+  const float dn = dh * (1.f - z), dz = dh * (hp - n);
+  const float dan = dn * (1.f - n * n);
+  const float dar = dan * hn * r * (1.f - r);
+  const float daz = dz * z * (1.f - z);
+  float* gi = dgi_t + (size_t)b * 3 * H;
+  float* gh = dgh_t + (size_t)b * 3 * H;
+  gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
+  gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = dan * r;
+  carry[q] = dh * z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Losses.  Thread (b, d) walks the time axis.
+//   phase 1: running mean of the predictions, masked residual, per-dimension sums / counts
+//   phase 2: gradient w.r.t. the per-step predictions (reverse running sum)
+__global__ void loss_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ x, float* __restrict__ diff,
+                                float* __restrict__ sum_sq_d, float* __restrict__ cnt_d, float* __restrict__ nz_rows,
+                                int L, int B, int D) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B * D) return;
+  const int b = q / D, d = q % D;
+  float cum = 0.f, s = 0.f, c = 0.f, nz = 0.f;
+  for (int t = 0; t + 1 < L; ++t) {
+    const size_t o = ((size_t)t * B + b) * D + d;
+    cum += mu[o];
+    const float avg = cum * (1.0f / (float)(t + 1));          // cumsum * (1/steps), uisrnn.py:265-271
+    const float truth = x[o + (size_t)B * D];                 // rnn_truth = rnn_input[1:]
+    const float pred = (truth != 0.f) ? avg : 0.f;            // (rnn_truth != 0) * mean
+    const float df = pred - truth;
+    diff[o] = df;
+    const float sq = df * df;
+    s += sq;
+    if (sq != 0.f) { c += 1.f; if (d == 0) nz += 1.f; }
+  }
+  atomicAdd(&sum_sq_d[d], s);
+  atomicAdd(&cnt_d[d], c);
+  if (d == 0) atomicAdd(nz_rows, nz);
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ diff, const float* __restrict__ sigma2,
+                                const float* __restrict__ nz_rows, float* __restrict__ dmu, int L, int B, int D) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B * D) return;
+  const int b = q / D, d = q % D;
+  const float w = 1.f / (2.f * sigma2[d]);
+  const float scale = 2.f * w / nz_rows[0];
+  float acc = 0.f;
+  dmu[((size_t)(L - 1) * B + b) * D + d] = 0.f;
+  for (int t = L - 2; t >= 0; --t) {
+    const size_t o = ((size_t)t * B + b) * D + d;
+    acc += diff[o] * scale * (1.0f / (float)(t + 1));
+    dmu[o] = acc;
+  }
+}
+
+// scalars[0..2] = loss1, loss2, loss3 ; g_sigma2 written into the gradient buffer
+__global__ void loss_scalar_kernel(const float* __restrict__ sum_sq_d, const float* __restrict__ cnt_d,
+                                   const float* __restrict__ nz_rows, const float* __restrict__ sigma2,
+                                   float sigma_alpha, float sigma_beta, float* __restrict__ g_sigma2,
+                                   float* __restrict__ scalars, int D) {
+  __shared__ float s1[256], s2[256];
+  float l1 = 0.f, l2 = 0.f;
+  const float nz = nz_rows[0];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float sg = sigma2[d], nd = cnt_d[d];
+    const float w = 1.f / (2.f * sg);
+    l1 += sum_sq_d[d] * w;
+    l2 += (2.f * sigma_alpha + nd + 2.f) / (2.f * nd) * logf(sg) + sigma_beta / (sg * nd);
+    g_sigma2[d] = -(sum_sq_d[d] / nz) / (2.f * sg * sg) + ((2.f * sigma_alpha + nd + 2.f) / (2.f * nd)) / sg -
+                  sigma_beta / (sg * sg * nd);
+  }
+  s1[threadIdx.x] = l1; s2[threadIdx.x] = l2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { scalars[0] = s1[0] / nz; scalars[1] = s2[0]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optimiser.  Parameters live in one flat buffer; segment s covers [seg_off[s], seg_off[s+1]).
+__global__ void seg_sumsq_kernel(const float* __restrict__ v, const int* __restrict__ seg_off, float* __restrict__ out) {
+  __shared__ float sh[256];
+  const int s = blockIdx.x;
+  float a = 0.f;
+  for (int i = seg_off[s] + threadIdx.x; i < seg_off[s + 1]; i += blockDim.x) a += v[i] * v[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[s] = sh[0];
+}
+
+// g += reg * p / ||p||  on the RNN segments (loss3 = reg * sum ||p||); scalars[2] = loss3
+__global__ void reg_grad_kernel(const float* __restrict__ p, float* __restrict__ g, const int* __restrict__ seg_off,
+                                const float* __restrict__ p_sumsq, float reg, int n_rnn_seg, float* __restrict__ scalars) {
+  const int s = blockIdx.y;
+  const float nrm = sqrtf(p_sumsq[s]);
+  const int i = seg_off[s] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < seg_off[s + 1]) g[i] += reg * p[i] / nrm;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    float l3 = 0.f;
+    for (int q = 0; q < n_rnn_seg; ++q) l3 += sqrtf(p_sumsq[q]);
+    scalars[2] = reg * l3;
+  }
+}
+
+// clip (RNN segments only, torch.nn.utils.clip_grad_norm_) + Adam (torch.optim.Adam defaults) + clamp
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, const float* __restrict__ g_sumsq, int n_rnn_seg, int rnn_end,
+                            int sigma_begin, int total, float max_norm, float step_size, float bc2_sqrt,
+                            int train_sigma2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (i >= sigma_begin && !train_sigma2) return;
+  float gi = g[i];
+  if (i < rnn_end) {
+    float tot = 0.f;
+    for (int q = 0; q < n_rnn_seg; ++q) tot += g_sumsq[q];
+    const float coef = fminf(max_norm / (sqrtf(tot) + 1e-6f), 1.0f);
+    gi *= coef;
+  }
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  float pi = p[i] - step_size * (mi / denom);
+  if (i >= sigma_begin) pi = fmaxf(pi, 1e-6f);  // self.sigma2.data.clamp_(min=1e-6), uisrnn.py:295
+  p[i] = pi;
+}
+
+struct DBuf {
+  float* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, (n + n / 8 + 64) * sizeof(float));
+    if (e != cudaSuccess) return api_fail(UIS_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    cap = n + n / 8 + 64;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <bool TA, bool TB>
+int gemm(cudaStream_t st, const float* A, const float* B, const float* bias, const float* mask, float* C, int M, int N,
+         int K, bool relu = false, bool acc = false) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0);
+  CUT(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace uis
+
+struct uis_trainer {
+  int device = 0, D = 0, H = 0;
+  uis_train_hparams hp{};
+  int seg_off_h[11];
+  int total = 0, rnn_end = 0, sigma_begin = 0;
+  long long step = 0;
+  uis::DBuf params, grads, m, v, segbuf;  // segbuf: seg_off (as int bits) is separate below
+  int* seg_off_d = nullptr;
+  float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 16][g_sumsq 16]
+  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry;
+};
+
+namespace {
+enum { SEG_WIH = 0, SEG_WHH, SEG_BIH, SEG_BHH, SEG_W1, SEG_B1, SEG_W2, SEG_B2, SEG_H0, SEG_SIGMA2, SEG_COUNT };
+}
+
+extern "C" {
+
+int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float* const* params /*[10] host*/,
+                       const uis_train_hparams* hp) {
+  if (!out || !params || !hp) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (D < 1 || H < 1 || H > 4096 || D > 4096) return uis::api_fail(UIS_ERR_INVALID, "bad shape");
+  CUT(cudaSetDevice(device));
+  uis_trainer* t = new uis_trainer();
+  t->device = device; t->D = D; t->H = H; t->hp = *hp;
+  const int sizes[SEG_COUNT] = {3 * H * D, 3 * H * H, 3 * H, 3 * H, H * H, H, D * H, D, H, D};
+  t->seg_off_h[0] = 0;
+  for (int s = 0; s < SEG_COUNT; ++s) t->seg_off_h[s + 1] = t->seg_off_h[s] + sizes[s];
+  t->total = t->seg_off_h[SEG_COUNT];
+  t->rnn_end = t->seg_off_h[SEG_H0];
+  t->sigma_begin = t->seg_off_h[SEG_SIGMA2];
+  auto body = [&]() -> int {
+    if (int rc = t->params.ensure(t->total)) return rc;
+    if (int rc = t->grads.ensure(t->total)) return rc;
+    if (int rc = t->m.ensure(t->total)) return rc;
+    if (int rc = t->v.ensure(t->total)) return rc;
+    for (int s = 0; s < SEG_COUNT; ++s) {
+      if (!params[s]) return uis::api_fail(UIS_ERR_INVALID, "NULL parameter %d", s);
+      CUT(cudaMemcpy(t->params.p + t->seg_off_h[s], params[s], (size_t)sizes[s] * 4, cudaMemcpyDefault));
+    }
+    CUT(cudaMemset(t->m.p, 0, (size_t)t->total * 4));
+    CUT(cudaMemset(t->v.p, 0, (size_t)t->total * 4));
+    CUT(cudaMalloc(&t->seg_off_d, sizeof(t->seg_off_h)));
+    CUT(cudaMemcpy(t->seg_off_d, t->seg_off_h, sizeof(t->seg_off_h), cudaMemcpyHostToDevice));
+    CUT(cudaMalloc(&t->small, (size_t)(2 * D + 64) * 4));
+    return 0;
+  };
+  if (int rc = body()) { uis_trainer_destroy(t); return rc; }
+  *out = t;
+  return 0;
+}
+
+int uis_trainer_destroy(uis_trainer* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->device);
+  uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
+                       &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry};
+  for (auto* b : bufs) b->release();
+  if (t->seg_off_d) cudaFree(t->seg_off_d);
+  if (t->small) cudaFree(t->small);
+  delete t;
+  return 0;
+}
+
+// One iteration.  x_host: fp32 [L][B][D] zero-padded batch (row 0 = zero frame), lengths[B] sorted
+// descending (each includes the zero frame).  mode 0: full step (forward, backward, clip, Adam);
+// mode 1: forward + backward only (gradients can be read back with uis_trainer_get, for tests).
+int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
+                     float* losses_out /*[3] host*/, void* stream) {
+  using namespace uis;
+  if (!t || !x_host || !lengths) return api_fail(UIS_ERR_INVALID, "null argument");
+  if (B < 1 || B > 32) return api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
+  if (L < 2) return api_fail(UIS_ERR_INVALID, "L < 2");
+  for (int b = 0; b < B; ++b) {
+    if (lengths[b] < 1 || lengths[b] > L || (b > 0 && lengths[b] > lengths[b - 1]) || (b == 0 && lengths[0] != L))
+      return api_fail(UIS_ERR_INVALID, "lengths must be sorted descending with lengths[0] == L");
+  }
+  CUT(cudaSetDevice(t->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = t->D, H = t->H;
+  const size_t R = (size_t)L * B;
+  if (int rc = t->x.ensure(R * D)) return rc;
+  if (int rc = t->gi.ensure(R * 3 * H)) return rc;
+  if (int rc = t->hs.ensure((R + B) * H)) return rc;
+  if (int rc = t->r.ensure(R * H)) return rc;
+  if (int rc = t->z.ensure(R * H)) return rc;
+  if (int rc = t->n.ensure(R * H)) return rc;
+  if (int rc = t->hn.ensure(R * H)) return rc;
+  if (int rc = t->a1.ensure(R * H)) return rc;
+  if (int rc = t->mu.ensure(R * D)) return rc;
+  if (int rc = t->diff.ensure(R * D)) return rc;
+  if (int rc = t->dmu.ensure(R * D)) return rc;
+  if (int rc = t->dz1.ensure(R * H)) return rc;
+  if (int rc = t->dout.ensure(R * H)) return rc;
+  if (int rc = t->dgi.ensure(R * 3 * H)) return rc;
+  if (int rc = t->dgh.ensure(R * 3 * H)) return rc;
+  if (int rc = t->carry.ensure((size_t)B * H)) return rc;
+  float* P = t->params.p;
+  float* G = t->grads.p;
+  const int* so = t->seg_off_h;
+  float* sum_sq_d = t->small; float* cnt_d = t->small + D; float* nz = t->small + 2 * D;
+  float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 16;
+  std::vector<int> nb(L);
+  for (int tt = 0; tt < L; ++tt) { int c = 0; while (c < B && lengths[c] > tt) ++c; nb[tt] = c; }
+
+  CUT(cudaMemcpyAsync(t->x.p, x_host, R * D * 4, cudaMemcpyHostToDevice, st));
+  CUT(cudaMemsetAsync(t->hs.p, 0, (R + B) * H * 4, st));
+  CUT(cudaMemsetAsync(t->small, 0, (size_t)(2 * D + 64) * 4, st));
+  CUT(cudaMemsetAsync(G, 0, (size_t)t->total * 4, st));
+  CUT(cudaMemsetAsync(t->carry.p, 0, (size_t)B * H * 4, st));
+  CUT(cudaMemsetAsync(t->dgi.p, 0, R * 3 * H * 4, st));
+  CUT(cudaMemsetAsync(t->dgh.p, 0, R * 3 * H * 4, st));
+  // h_{-1} = rnn_init_hidden repeated over the batch (uisrnn.py:262)
+  for (int b = 0; b < B; ++b)
+    CUT(cudaMemcpyAsync(t->hs.p + (size_t)b * H, P + so[SEG_H0], (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- forward
+  if (int rc = gemm<false, true>(st, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
+  const size_t fwd_smem = (size_t)H * 33 * 4;
+  CUT(cudaFuncSetAttribute(gru_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  for (int tt = 0; tt < L; ++tt) {
+    const size_t o = (size_t)tt * B;
+    gru_fwd_step_kernel<<<(H + 7) / 8, 256, fwd_smem, st>>>(P + so[SEG_WHH], P + so[SEG_BHH], t->gi.p + o * 3 * H,
+                                                           t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
+                                                           t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, B, nb[tt], H);
+  }
+  CUT(cudaGetLastError());
+  const float* out = t->hs.p + (size_t)B * H;  // out[t] = h_t ; padded rows stay zero
+  if (int rc = gemm<false, true>(st, out, P + so[SEG_W1], P + so[SEG_B1], nullptr, t->a1.p, (int)R, H, H, true)) return rc;
+  if (int rc = gemm<false, true>(st, t->a1.p, P + so[SEG_W2], P + so[SEG_B2], nullptr, t->mu.p, (int)R, D, H)) return rc;
+  const int bd_blocks = (B * D + 255) / 256;
+  loss_fwd_kernel<<<bd_blocks, 256, 0, st>>>(t->mu.p, t->x.p, t->diff.p, sum_sq_d, cnt_d, nz, L, B, D);
+  loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
+                                       G + so[SEG_SIGMA2], scalars, D);
+  // ---- backward
+  loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[SEG_SIGMA2], nz, t->dmu.p, L, B, D);
+  CUT(cudaGetLastError());
+  if (int rc = gemm<true, false>(st, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[SEG_W2], D, H, (int)R)) return rc;
+  colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(t->dmu.p, G + so[SEG_B2], (int)R, D);
+  if (int rc = gemm<false, false>(st, t->dmu.p, P + so[SEG_W2], nullptr, t->a1.p, t->dz1.p, (int)R, H, D)) return rc;  // * relu'
+  if (int rc = gemm<true, false>(st, t->dz1.p, out, nullptr, nullptr, G + so[SEG_W1], H, H, (int)R)) return rc;
+  colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dz1.p, G + so[SEG_B1], (int)R, H);
+  if (int rc = gemm<false, false>(st, t->dz1.p, P + so[SEG_W1], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
+  for (int tt = L - 1; tt >= 0; --tt) {
+    if (nb[tt] == 0) continue;
+    const size_t o = (size_t)tt * B;
+    gru_bwd_step_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->dout.p + o * H, t->carry.p, t->r.p + o * H,
+                                                                  t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H,
+                                                                  t->hs.p + o * H, t->dgi.p + o * 3 * H,
+                                                                  t->dgh.p + o * 3 * H, nb[tt], H);
+    // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
+    if (int rc = gemm<false, false>(st, t->dgh.p + o * 3 * H, P + so[SEG_WHH], nullptr, nullptr, t->carry.p, nb[tt], H,
+                                    3 * H, false, true))
+      return rc;
+  }
+  CUT(cudaGetLastError());
+  if (int rc = gemm<true, false>(st, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
+  if (int rc = gemm<true, false>(st, t->dgh.p, t->hs.p, nullptr, nullptr, G + so[SEG_WHH], 3 * H, H, (int)R)) return rc;
+  colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgi.p, G + so[SEG_BIH], (int)R, 3 * H);
+  colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[SEG_BHH], (int)R, 3 * H);
+  colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[SEG_H0], B, H);  // d h0 = sum_b d h_{-1}
+  // regulariser gradient + loss3
+  seg_sumsq_kernel<<<8, 256, 0, st>>>(P, t->seg_off_d, p_sumsq);
+  {
+    int maxseg = 0;
+    for (int s = 0; s < 8; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
+    dim3 grid((maxseg + 255) / 256, 8);
+    reg_grad_kernel<<<grid, 256, 0, st>>>(P, G, t->seg_off_d, p_sumsq, t->hp.regularization_weight, 8, scalars);
+  }
+  CUT(cudaGetLastError());
+  if (mode == 0) {
+    seg_sumsq_kernel<<<8, 256, 0, st>>>(G, t->seg_off_d, g_sumsq);
+    t->step += 1;
+    // torch.optim.Adam (defaults): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles
+    const double bc1 = 1.0 - std::pow(0.9, (double)t->step), bc2 = 1.0 - std::pow(0.999, (double)t->step);
+    adam_kernel<<<(t->total + 255) / 256, 256, 0, st>>>(P, G, t->m.p, t->v.p, g_sumsq, 8, t->rnn_end, t->sigma_begin,
+                                                        t->total, t->hp.grad_max_norm,
+                                                        (float)((double)t->hp.learning_rate / bc1),
+                                                        (float)std::sqrt(bc2), t->hp.train_sigma2);
+    CUT(cudaGetLastError());
+  }
+  if (losses_out) {
+    CUT(cudaMemcpyAsync(losses_out, scalars, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUT(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// what: 0 = parameters, 1 = gradients of the last step.  out[10] host buffers (any may be NULL).
+int uis_trainer_get(uis_trainer* t, int what, float* const* out) {
+  if (!t || !out) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  CUT(cudaSetDevice(t->device));
+  CUT(cudaDeviceSynchronize());
+  const float* src = what == 0 ? t->params.p : t->grads.p;
+  for (int s = 0; s < SEG_COUNT; ++s)
+    if (out[s])
+      CUT(cudaMemcpy(out[s], src + t->seg_off_h[s], (size_t)(t->seg_off_h[s + 1] - t->seg_off_h[s]) * 4,
+                     cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -56,7 +56,19 @@ class Stats(C.Structure):
 # Every symbol include/uisrnn_b200.h declares (tests check the .so exports all of them).
 EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destroy',
            'uis_model_constants', 'uis_predict', 'uis_predict_device',
-           'uis_predict_workspace_bytes', 'uis_get_stats')
+           'uis_predict_workspace_bytes', 'uis_get_stats', 'uis_trainer_create',
+           'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get')
+
+
+class TrainHParams(C.Structure):
+  _fields_ = [('learning_rate', C.c_float), ('sigma_alpha', C.c_float), ('sigma_beta', C.c_float),
+              ('regularization_weight', C.c_float), ('grad_max_norm', C.c_float),
+              ('train_sigma2', C.c_int32)]
+
+
+PARAM_ORDER = ('gru.weight_ih_l0', 'gru.weight_hh_l0', 'gru.bias_ih_l0', 'gru.bias_hh_l0',
+               'linear_mean1.weight', 'linear_mean1.bias', 'linear_mean2.weight', 'linear_mean2.bias',
+               'rnn_init_hidden', 'sigma2')
 
 _lib = None
 
@@ -94,6 +106,16 @@ def load_library():
                                               C.POINTER(PredictOpts)]
   lib.uis_get_stats.restype = C.c_int
   lib.uis_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+  lib.uis_trainer_create.restype = C.c_int
+  lib.uis_trainer_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p), C.POINTER(TrainHParams)]
+  lib.uis_trainer_destroy.restype = C.c_int
+  lib.uis_trainer_destroy.argtypes = [C.c_void_p]
+  lib.uis_trainer_step.restype = C.c_int
+  lib.uis_trainer_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int,
+                                   fp, C.c_void_p]
+  lib.uis_trainer_get.restype = C.c_int
+  lib.uis_trainer_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
   del ip
   _lib = lib
   return lib
@@ -229,3 +251,61 @@ class NativeModel:
     s = Stats()
     _check(self._lib, self._lib.uis_get_stats(self._h, C.byref(s)))
     return s.as_dict()
+
+
+class NativeTrainer:
+  """Owns a `uis_trainer*`: parameters, gradients and Adam state of one fit_concatenated call live
+  on the device; `step()` runs one iteration on a host batch.  `params`: dict name -> ndarray in
+  PARAM_ORDER (rnn_init_hidden flattened to [H])."""
+
+  def __init__(self, params, hparams, device=0):
+    lib = load_library()
+    self._lib = lib
+    self._h = C.c_void_p()
+    self.shapes = [tuple(np.asarray(params[k]).shape) for k in PARAM_ORDER]
+    arrs = [_f32(np.asarray(params[k]).reshape(-1)) for k in PARAM_ORDER]
+    self.H = int(np.asarray(params['linear_mean1.weight']).shape[0])
+    self.D = int(np.asarray(params['linear_mean2.weight']).shape[0])
+    ptrs = (C.c_void_p * 10)(*[a.ctypes.data for a in arrs])
+    hp = TrainHParams(float(hparams['learning_rate']), float(hparams['sigma_alpha']),
+                      float(hparams['sigma_beta']), float(hparams['regularization_weight']),
+                      float(hparams['grad_max_norm']), int(bool(hparams['train_sigma2'])))
+    _check(lib, lib.uis_trainer_create(C.byref(self._h), device, self.D, self.H, ptrs, C.byref(hp)))
+
+  def close(self):
+    if getattr(self, '_h', None) is not None and self._h:
+      self._lib.uis_trainer_destroy(self._h)
+      self._h = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  def step(self, rnn_input, lengths, grads_only=False, stream=0):
+    """rnn_input: float32 [L, B, D] zero-padded time-major batch; lengths: [B] descending.
+    Returns (loss1, loss2, loss3)."""
+    x = _f32(rnn_input)
+    L, B, D = x.shape
+    assert D == self.D
+    lens = np.ascontiguousarray(lengths, dtype=np.int32)
+    losses = np.zeros(3, np.float32)
+    rc = self._lib.uis_trainer_step(self._h, x.ctypes.data_as(C.c_void_p),
+                                    lens.ctypes.data_as(C.POINTER(C.c_int32)), B, L,
+                                    1 if grads_only else 0, losses.ctypes.data_as(C.POINTER(C.c_float)),
+                                    C.c_void_p(stream))
+    _check(self._lib, rc)
+    return tuple(float(v) for v in losses)
+
+  def _get(self, what):
+    outs = [np.empty(int(np.prod(s)) if s else 1, np.float32) for s in self.shapes]
+    ptrs = (C.c_void_p * 10)(*[o.ctypes.data for o in outs])
+    _check(self._lib, self._lib.uis_trainer_get(self._h, what, ptrs))
+    return {k: o.reshape(s) for k, o, s in zip(PARAM_ORDER, outs, self.shapes)}
+
+  def parameters(self):
+    return self._get(0)
+
+  def gradients(self):
+    return self._get(1)

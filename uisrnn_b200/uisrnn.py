@@ -174,6 +174,9 @@ class UISRNN:
     optimizer = self._get_optimizer(optimizer=args.optimizer, learning_rate=args.learning_rate)
     sub_sequences, seq_lengths = utils.resize_sequence(
         sequence=train_sequence, cluster_id=train_cluster_id, num_permutations=args.num_permutations)
+    if self._native_fit_supported(args):
+      self._fit_native(sub_sequences, seq_lengths, args)
+      return
     batch = None
     if args.batch_size is None:  # "batch learning": one fixed batch holding every sub-sequence
       batch = utils.pack_sequence(sub_sequences, seq_lengths, None, self.observation_dim, self.device)
@@ -207,6 +210,49 @@ class UISRNN:
             2, 'Iter: {:d}  \tTraining Loss: {:.4f}    \n    Negative Log Likelihood: {:.4f}\t'
                'Sigma2 Prior: {:.4f}\tRegularization: {:.4f}'.format(
                    num_iter, float(loss.data), float(loss1.data), float(loss2.data), float(loss3.data)))
+    self._native = None
+    self.logger.print(1, 'Done training with {} iterations'.format(args.train_iteration))
+
+  def _native_fit_supported(self, args):
+    """The hand-written training kernels (csrc/uis_train.cu) cover the default model family:
+    CUDA device, one GRU layer, mini-batches of 1..32 sequences.  Other configurations train with
+    PyTorch autograd on the model's device (same mathematics)."""
+    import os
+    return (self.device.type == 'cuda' and self.rnn_init_hidden.shape[0] == 1 and
+            args.batch_size is not None and 1 <= args.batch_size <= 32 and
+            os.environ.get('UISRNN_B200_TORCH_FIT', '0') != '1')
+
+  def _fit_native(self, sub_sequences, seq_lengths, args):
+    """fit_concatenated's iteration loop (uisrnn.py:252-311) on libuisrnn_b200.so: parameters,
+    gradients and Adam state stay on the device; per iteration only the batch goes up and three
+    loss scalars come back."""
+    from . import native
+    state = {k: v.detach().cpu().numpy() for k, v in self.rnn_model.state_dict().items()}
+    params = {name: state[name] for name in native.PARAM_ORDER[:8]}
+    params['rnn_init_hidden'] = self.rnn_init_hidden.detach().cpu().numpy().reshape(-1)
+    params['sigma2'] = self.sigma2.detach().cpu().numpy()
+    hparams = {'learning_rate': args.learning_rate, 'sigma_alpha': args.sigma_alpha, 'sigma_beta': args.sigma_beta,
+               'regularization_weight': args.regularization_weight, 'grad_max_norm': args.grad_max_norm,
+               'train_sigma2': self.estimate_sigma2}
+    trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
+    self.last_training_losses = []
+    try:
+      for num_iter in range(args.train_iteration):
+        rnn_input, lengths = utils.pack_batch(sub_sequences, seq_lengths, args.batch_size, self.observation_dim)
+        loss1, loss2, loss3 = trainer.step(rnn_input.astype(np.float32), lengths)
+        self.last_training_losses.append(loss1)
+        if num_iter % 10 == 0 or num_iter == args.train_iteration - 1:
+          self.logger.print(
+              2, 'Iter: {:d}  \tTraining Loss: {:.4f}    \n    Negative Log Likelihood: {:.4f}\t'
+                 'Sigma2 Prior: {:.4f}\tRegularization: {:.4f}'.format(
+                     num_iter, loss1 + loss2 + loss3, loss1, loss2, loss3))
+      trained = trainer.parameters()
+    finally:
+      trainer.close()
+    with torch.no_grad():
+      self.rnn_model.load_state_dict({k: torch.from_numpy(trained[k].copy()) for k in native.PARAM_ORDER[:8]})
+      self.rnn_init_hidden.data.copy_(torch.from_numpy(trained['rnn_init_hidden'].reshape(1, 1, -1)))
+      self.sigma2.data.copy_(torch.from_numpy(trained['sigma2']))
     self._native = None
     self.logger.print(1, 'Done training with {} iterations'.format(args.train_iteration))
 

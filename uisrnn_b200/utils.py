@@ -109,11 +109,10 @@ def resize_sequence(sequence, cluster_id, num_permutations=None):
   return sub_sequences, seq_lengths
 
 
-def pack_sequence(sub_sequences, seq_lengths, batch_size, observation_dim, device):
-  """Builds one training batch (utils.py:204-250): `np.random.choice(num_clusters, batch_size)`
-  (with replacement) over the sub-sequences sorted by decreasing length, a zero frame prepended,
-  zero padded to the longest, packed for the GRU.  Returns `(packed_rnn_input, rnn_truth)` with
-  `rnn_truth = rnn_input[1:]`."""
+def pack_batch(sub_sequences, seq_lengths, batch_size, observation_dim):
+  """The host half of `pack_sequence`: draws the batch (same `np.random.choice` call as
+  utils.py:237) and returns `(rnn_input float64 [L, B, D] zero-padded time-major, lengths [B])`,
+  lengths sorted descending and counting the leading zero frame."""
   seq_lengths = np.asarray(seq_lengths)
   num_clusters = len(seq_lengths)
   sorted_lengths = np.sort(seq_lengths)[::-1]
@@ -128,6 +127,15 @@ def pack_sequence(sub_sequences, seq_lengths, batch_size, observation_dim, devic
   rnn_input = np.zeros((lengths[0], width, observation_dim))
   for column, pick in enumerate(chosen):
     rnn_input[1:sorted_lengths[pick], column, :] = sub_sequences[permute_index[pick]]
+  return rnn_input, np.ascontiguousarray(lengths)
+
+
+def pack_sequence(sub_sequences, seq_lengths, batch_size, observation_dim, device):
+  """Builds one training batch (utils.py:204-250): `np.random.choice(num_clusters, batch_size)`
+  (with replacement) over the sub-sequences sorted by decreasing length, a zero frame prepended,
+  zero padded to the longest, packed for the GRU.  Returns `(packed_rnn_input, rnn_truth)` with
+  `rnn_truth = rnn_input[1:]`."""
+  rnn_input, lengths = pack_batch(sub_sequences, seq_lengths, batch_size, observation_dim)
   rnn_input = torch.from_numpy(rnn_input).float().to(device)
   packed_rnn_input = torch.nn.utils.rnn.pack_padded_sequence(
       rnn_input, np.ascontiguousarray(lengths), batch_first=False)
