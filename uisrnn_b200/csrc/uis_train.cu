@@ -118,40 +118,91 @@ __global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------
-// GRU forward, one time step: for b < nb, j < H
-//   gh = W_hh h_{t-1} + b_hh ; r,z = sigmoid(gi + gh) ; n = tanh(gi_n + r * gh_n) ; h = (h_prev - n) z + n
-// Block = (8 hidden units) x (32 sequences); h_prev staged transposed in shared memory.
-__global__ void __launch_bounds__(256) gru_fwd_step_kernel(const float* __restrict__ whh, const float* __restrict__ bhh,
-                                                           const float* __restrict__ gi_t, const float* __restrict__ hprev,
-                                                           float* __restrict__ hnew, float* __restrict__ r_t,
-                                                           float* __restrict__ z_t, float* __restrict__ n_t,
-                                                           float* __restrict__ hn_t, int B, int nb, int H) {
-  extern __shared__ float hs[];  // [H][33]
-  const int tid = threadIdx.x;
-  for (int q = tid; q < nb * H; q += 256) {
-    const int b = q / H, k = q % H;
-    hs[k * 33 + b] = hprev[(size_t)b * H + k];
+// Recurrent products: C[b][n] (+)= sum_k A[b][k] * W[k][n]   for b < nb <= 32 (one time step).
+// Lane = output column n (coalesced W rows), 32 accumulators per thread (one per sequence), the
+// K dimension split over the 8 warps of the CTA and reduced through shared memory.  A is read with
+// warp-uniform 128-bit loads (L1 broadcast).  Grid = N / 32 CTAs.
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, int lda,
+                                                          const float* __restrict__ W, float* __restrict__ C,
+                                                          int ldc, int nb, int N, int K, int accumulate) {
+  __shared__ float part[8][32][33];
+  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + lane;
+  const int kslice = (K + 7) / 8;
+  const int k0 = w * kslice, k1 = min(K, k0 + kslice);
+  float acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+  if (n < N) {
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      const float w0 = W[(size_t)k * N + n], w1 = W[(size_t)(k + 1) * N + n];
+      const float w2 = W[(size_t)(k + 2) * N + n], w3 = W[(size_t)(k + 3) * N + n];
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        if (b < nb) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * lda + k));
+          acc[b] = fmaf(a.x, w0, acc[b]); acc[b] = fmaf(a.y, w1, acc[b]);
+          acc[b] = fmaf(a.z, w2, acc[b]); acc[b] = fmaf(a.w, w3, acc[b]);
+        }
+      }
+    }
+    for (; k < k1; ++k) {
+      const float w0 = W[(size_t)k * N + n];
+#pragma unroll
+      for (int b = 0; b < 32; ++b)
+        if (b < nb) acc[b] = fmaf(__ldg(A + (size_t)b * lda + k), w0, acc[b]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 32; ++b) part[w][b][lane] = acc[b];
+  __syncthreads();
+  // thread (b = tid / 8 .., ) : 256 threads sum 32 x 32 outputs, 4 each
+  for (int q = threadIdx.x; q < 32 * 32; q += 256) {
+    const int b = q / 32, l = q % 32;
+    const int nn = blockIdx.x * 32 + l;
+    if (b < nb && nn < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) v += part[ww][b][l];
+      float* dst = C + (size_t)b * ldc + nn;
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
+}
+
+// GRU gates of one time step (PyTorch order r,z,n):  gh = W_hh h_{t-1} (no bias yet), b < nb
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ gh, const float* __restrict__ bhh,
+                                    const float* __restrict__ gi_t, const float* __restrict__ hprev,
+                                    float* __restrict__ hnew, float* __restrict__ r_t, float* __restrict__ z_t,
+                                    float* __restrict__ n_t, float* __restrict__ hn_t, int nb, int H) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb * H) return;
+  const int b = q / H, j = q % H;
+  const float* g = gh + (size_t)b * 3 * H;
+  const float* gi = gi_t + (size_t)b * 3 * H;
+  const float r = sigmoid_f32(gi[j] + (g[j] + bhh[j]));
+  const float z = sigmoid_f32(gi[H + j] + (g[H + j] + bhh[H + j]));
+  const float hn = g[2 * H + j] + bhh[2 * H + j];
+  const float n = tanhf(gi[2 * H + j] + r * hn);
+  const float hp = hprev[q];
+  hnew[q] = (hp - n) * z + n;
+  r_t[q] = r; z_t[q] = z; n_t[q] = n; hn_t[q] = hn;
+}
+
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cn) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cn) tile[i][threadIdx.x] = in[(size_t)r * Cn + c];
   }
   __syncthreads();
-  const int b = tid % 32, j = blockIdx.x * 8 + tid / 32;
-  if (b >= nb || j >= H) return;
-  const float* wr = whh + (size_t)j * H;
-  const float* wz = whh + (size_t)(H + j) * H;
-  const float* wn = whh + (size_t)(2 * H + j) * H;
-  float ar = 0.f, az = 0.f, an = 0.f;
-  for (int k = 0; k < H; ++k) {
-    const float h = hs[k * 33 + b];
-    ar = fmaf(wr[k], h, ar); az = fmaf(wz[k], h, az); an = fmaf(wn[k], h, an);
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cn) out[(size_t)c * R + r] = tile[threadIdx.x][i];
   }
-  const float* gi = gi_t + (size_t)b * 3 * H;
-  const float r = sigmoid_f32(gi[j] + (ar + bhh[j]));
-  const float z = sigmoid_f32(gi[H + j] + (az + bhh[H + j]));
-  const float hn = an + bhh[2 * H + j];
-  const float n = tanhf(gi[2 * H + j] + r * hn);
-  const float hp = hs[j * 33 + b];
-  const size_t o = (size_t)b * H + j;
-  hnew[o] = (hp - n) * z + n;
-  r_t[o] = r; z_t[o] = z; n_t[o] = n; hn_t[o] = hn;
 }
 
 // GRU backward, elementwise part of one time step (b < nb):
@@ -248,14 +299,28 @@ __global__ void loss_scalar_kernel(const float* __restrict__ sum_sq_d, const flo
 
 // ---------------------------------------------------------------------------------------------
 // Optimiser.  Parameters live in one flat buffer; segment s covers [seg_off[s], seg_off[s+1]).
-__global__ void seg_sumsq_kernel(const float* __restrict__ v, const int* __restrict__ seg_off, float* __restrict__ out) {
+// grid (kSumsqBlocks, segments): partial[s][blockIdx.x]; then one block per segment folds the partials
+constexpr int kSumsqBlocks = 64;
+__global__ void seg_sumsq_partial_kernel(const float* __restrict__ v, const int* __restrict__ seg_off,
+                                         float* __restrict__ partial) {
   __shared__ float sh[256];
-  const int s = blockIdx.x;
+  const int s = blockIdx.y;
   float a = 0.f;
-  for (int i = seg_off[s] + threadIdx.x; i < seg_off[s + 1]; i += blockDim.x) a += v[i] * v[i];
+  for (int i = seg_off[s] + blockIdx.x * 256 + threadIdx.x; i < seg_off[s + 1]; i += kSumsqBlocks * 256) a += v[i] * v[i];
   sh[threadIdx.x] = a;
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[s * kSumsqBlocks + blockIdx.x] = sh[0];
+}
+__global__ void seg_sumsq_final_kernel(const float* __restrict__ partial, float* __restrict__ out) {
+  __shared__ float sh[kSumsqBlocks];
+  const int s = blockIdx.x;
+  sh[threadIdx.x] = partial[s * kSumsqBlocks + threadIdx.x];
+  __syncthreads();
+  for (int o = kSumsqBlocks / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
@@ -268,7 +333,7 @@ __global__ void reg_grad_kernel(const float* __restrict__ p, float* __restrict__
   const int s = blockIdx.y;
   const float nrm = sqrtf(p_sumsq[s]);
   const int i = seg_off[s] + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg_off[s + 1]) g[i] += reg * p[i] / nrm;
+  if (i < seg_off[s + 1] && nrm > 0.f) g[i] += reg * p[i] / nrm;  // torch.norm'(0) = 0
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     float l3 = 0.f;
     for (int q = 0; q < n_rnn_seg; ++q) l3 += sqrtf(p_sumsq[q]);
@@ -337,7 +402,7 @@ struct uis_trainer {
   uis::DBuf params, grads, m, v, segbuf;  // segbuf: seg_off (as int bits) is separate below
   int* seg_off_d = nullptr;
   float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 16][g_sumsq 16]
-  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry;
+  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial;
 };
 
 namespace {
@@ -385,7 +450,8 @@ int uis_trainer_destroy(uis_trainer* t) {
   if (!t) return 0;
   cudaSetDevice(t->device);
   uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
-                       &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry};
+                       &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
+                       &t->partial};
   for (auto* b : bufs) b->release();
   if (t->seg_off_d) cudaFree(t->seg_off_d);
   if (t->small) cudaFree(t->small);
@@ -426,6 +492,9 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   if (int rc = t->dgi.ensure(R * 3 * H)) return rc;
   if (int rc = t->dgh.ensure(R * 3 * H)) return rc;
   if (int rc = t->carry.ensure((size_t)B * H)) return rc;
+  if (int rc = t->whh_t.ensure((size_t)3 * H * H)) return rc;
+  if (int rc = t->ghbuf.ensure((size_t)32 * 3 * H)) return rc;
+  if (int rc = t->partial.ensure((size_t)16 * kSumsqBlocks)) return rc;
   float* P = t->params.p;
   float* G = t->grads.p;
   const int* so = t->seg_off_h;
@@ -447,13 +516,18 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
 
   // ---- forward
   if (int rc = gemm<false, true>(st, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
-  const size_t fwd_smem = (size_t)H * 33 * 4;
-  CUT(cudaFuncSetAttribute(gru_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  {  // k-major copy of W_hh for the recurrent products (the weights change every iteration)
+    dim3 tg((H + 31) / 32, (3 * H + 31) / 32), tb(32, 8);
+    transpose_kernel<<<tg, tb, 0, st>>>(P + so[SEG_WHH], t->whh_t.p, 3 * H, H);
+  }
   for (int tt = 0; tt < L; ++tt) {
+    if (nb[tt] == 0) break;
     const size_t o = (size_t)tt * B;
-    gru_fwd_step_kernel<<<(H + 7) / 8, 256, fwd_smem, st>>>(P + so[SEG_WHH], P + so[SEG_BHH], t->gi.p + o * 3 * H,
-                                                           t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
-                                                           t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, B, nb[tt], H);
+    skinny_gemm_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H, nb[tt], 3 * H,
+                                                          H, 0);
+    gru_gate_fwd_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, P + so[SEG_BHH], t->gi.p + o * 3 * H,
+                                                                  t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
+                                                                  t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, nb[tt], H);
   }
   CUT(cudaGetLastError());
   const float* out = t->hs.p + (size_t)B * H;  // out[t] = h_t ; padded rows stay zero
@@ -480,9 +554,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
                                                                   t->hs.p + o * H, t->dgi.p + o * 3 * H,
                                                                   t->dgh.p + o * 3 * H, nb[tt], H);
     // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
-    if (int rc = gemm<false, false>(st, t->dgh.p + o * 3 * H, P + so[SEG_WHH], nullptr, nullptr, t->carry.p, nb[tt], H,
-                                    3 * H, false, true))
-      return rc;
+    skinny_gemm_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p, H, nb[tt], H,
+                                                      3 * H, 1);
   }
   CUT(cudaGetLastError());
   if (int rc = gemm<true, false>(st, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
@@ -491,7 +564,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[SEG_BHH], (int)R, 3 * H);
   colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[SEG_H0], B, H);  // d h0 = sum_b d h_{-1}
   // regulariser gradient + loss3
-  seg_sumsq_kernel<<<8, 256, 0, st>>>(P, t->seg_off_d, p_sumsq);
+  seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(P, t->seg_off_d, t->partial.p);
+  seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, p_sumsq);
   {
     int maxseg = 0;
     for (int s = 0; s < 8; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
@@ -500,7 +574,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   }
   CUT(cudaGetLastError());
   if (mode == 0) {
-    seg_sumsq_kernel<<<8, 256, 0, st>>>(G, t->seg_off_d, g_sumsq);
+    seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(G, t->seg_off_d, t->partial.p);
+    seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, g_sumsq);
     t->step += 1;
     // torch.optim.Adam (defaults): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles
     const double bc1 = 1.0 - std::pow(0.9, (double)t->step), bc2 = 1.0 - std::pow(0.999, (double)t->step);
