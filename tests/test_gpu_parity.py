@@ -167,3 +167,43 @@ def test_wide_beam_look_ahead_config3_shape(toy_model):
   x = synth_utt(1234, n_frames=24)[0]
   got = toy_model.predict([x], beam_size=30, look_ahead=2, test_iteration=2)[0]
   assert got.tolist() == uis_oracle.predict_single(om, x, beam_size=30, look_ahead=2, test_iteration=2)
+
+
+def _random_weights(H, D, seed, scale=1.0):
+  """A synthetic (untrained) model: small recurrent weights so hidden states stay informative."""
+  rng = np.random.default_rng(seed)
+  u = lambda *s: (rng.uniform(-1, 1, size=s) * scale / np.sqrt(H)).astype(np.float32)
+  return {'depth': 1, 'weight_ih_l0': u(3 * H, D), 'weight_hh_l0': u(3 * H, H), 'bias_ih_l0': u(3 * H),
+          'bias_hh_l0': u(3 * H), 'w1': u(H, H), 'b1': u(H), 'w2': u(D, H), 'b2': u(D),
+          'h0': u(1, 1, H), 'sigma2': (0.05 + 0.1 * rng.random(D)).astype(np.float32),
+          'transition_bias': 0.2, 'crp_alpha': 0.7}
+
+
+@pytest.mark.parametrize('H,D', [(256, 128), (128, 64), (512, 256)])
+def test_random_models_all_kernel_shapes_match_oracle(native, H, D):
+  """Every instantiated (hidden, dim) pair, untrained weights (cluster counts grow quickly here, so
+  the table-overflow path and many-cluster scoring are exercised), crp_alpha != 1."""
+  w = _random_weights(H, D, seed=H + D)
+  model = native.NativeModel(w)
+  om = uis_oracle.OracleModel(w)
+  rng = np.random.default_rng(7)
+  xs = [rng.standard_normal((n, D)) * 0.3 for n in (17, 5, 26)]
+  for beam, la in ((10, 1), (4, 2)):
+    try:
+      got = model.predict(xs, beam_size=beam, look_ahead=la, test_iteration=2, kcap=64 if la == 1 else 48)
+    except native.NativeError as err:  # a legitimately huge tree is reported, never mis-computed
+      assert err.code in (native.UIS_ERR_CAPACITY, native.UIS_ERR_OVERFLOW)
+      continue
+    for x, o in zip(xs, got):
+      assert o.tolist() == uis_oracle.predict_single(om, x, beam_size=beam, look_ahead=la, test_iteration=2)
+
+
+def test_test_iteration_is_tiling_full_size(toy_model):
+  """Full-size property check (no oracle): test_iteration=2 must equal decoding the utterance
+  concatenated with itself at test_iteration=1 and keeping the labels of the last copy
+  (uisrnn.py:524, :561)."""
+  from uisrnn_b200.synth import synth_utt
+  x = synth_utt(4321, n_frames=700)[0]
+  twice = toy_model.predict([np.concatenate([x, x])], test_iteration=1)[0]
+  tiled = toy_model.predict([x], test_iteration=2)[0]
+  assert tiled.tolist() == twice[700:].tolist()
