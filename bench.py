@@ -105,6 +105,69 @@ def load_peaks():
   return 6650.0, 'fallback (B200_PROFILING.md)', 1965.0
 
 
+def measured_traffic(utts):
+  """DRAM bytes per launch of the beam kernel from the committed ncu capture (profiles/r1_traffic.json);
+  only valid for the workload it was captured on."""
+  path = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+  try:
+    with open(path) as f:
+      d = json.load(f)
+    if d['utterances'] == utts and d['frames_per_utterance'] == N_FRAMES:
+      return d['dram_bytes_read'] + d['dram_bytes_write']
+  except Exception:  # pylint: disable=broad-except
+    pass
+  return None
+
+
+def secondary_metrics(model, torch):
+  """Best-effort extra numbers for the other BASELINE configs (never allowed to break the headline line)."""
+  out = {}
+  try:  # config 3: beam_size=30, look_ahead=2 (wide-beam stress), device-resident, 148 x 100 frames
+    from uisrnn_b200.synth import synth_utt
+    U3, N3 = 148, 100
+    x3 = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N3, dim=DIM)[0] for u in range(U3)]).astype(np.float32)).cuda()
+    lab3 = torch.empty(U3 * N3, dtype=torch.int32, device='cuda')
+    off3 = np.arange(U3 + 1, dtype=np.int64) * N3
+    for _ in range(2):
+      model.predict_device(x3.data_ptr(), off3, lab3.data_ptr(), beam_size=30, look_ahead=2, test_iteration=TEST_ITER)
+      st3 = model.stats()
+    out['config3_beam30_lookahead2'] = {'frames_per_s': U3 * N3 / (st3['beam_ms'] / 1e3), 'kernel_ms': st3['beam_ms'],
+                                        'gru_columns_per_step': st3['gru_columns'] / max(1, st3['beam_steps'])}
+  except Exception as err:  # pylint: disable=broad-except
+    out['config3_beam30_lookahead2'] = {'error': str(err)[:200]}
+  try:  # config 4: fit() iteration on 50k concatenated frames, batch_size=32 (device trainer, csrc/uis_train.cu)
+    import random
+    from uisrnn_b200 import native, utils
+    from uisrnn_b200.synth import synth_training_set
+    np.random.seed(0); random.seed(0)
+    seqs, ids = synth_training_set(2000, 500, n_frames=100, dim=DIM, n_spk=3)
+    xcat, ycat = utils.concatenate_training_data(seqs, ids, True, True)
+    subs, lens = utils.resize_sequence(xcat, np.array(ycat), 10)
+    w = dict(np.load(MODEL_FIXTURE))
+    params = {'gru.weight_ih_l0': w['weight_ih_l0'], 'gru.weight_hh_l0': w['weight_hh_l0'], 'gru.bias_ih_l0': w['bias_ih_l0'],
+              'gru.bias_hh_l0': w['bias_hh_l0'], 'linear_mean1.weight': w['w1'], 'linear_mean1.bias': w['b1'],
+              'linear_mean2.weight': w['w2'], 'linear_mean2.bias': w['b2'], 'rnn_init_hidden': w['h0'].reshape(-1),
+              'sigma2': w['sigma2']}
+    hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5,
+          'grad_max_norm': 5.0, 'train_sigma2': True}
+    tr = native.NativeTrainer(params, hp)
+    iters, rows = 30, 0
+    for i in range(3 + iters):
+      if i == 3:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+      xi, li = utils.pack_batch(subs, lens, 32, DIM)
+      if i >= 3:
+        rows += int(li.sum())
+      tr.step(xi.astype(np.float32), li)
+    dt = time.perf_counter() - t0
+    out['config4_fit_batch32'] = {'ms_per_iteration': 1e3 * dt / iters, 'packed_rows_per_s': rows / dt,
+                                  'includes': 'host batch packing + H2D + forward/backward/clip/Adam kernels'}
+    tr.close()
+  except Exception as err:  # pylint: disable=broad-except
+    out['config4_fit_batch32'] = {'error': str(err)[:200]}
+  return out
+
+
 def cpu_baseline_port(n_utts=3):
   """Times the CPU oracle port (numpy, 1 thread of control) on a bounded sample."""
   sys.path.insert(0, os.path.join(ROOT, 'oracle'))
@@ -328,16 +391,20 @@ def run_b200(args):
               'path': 'uisrnn.UISRNN.predict(list of pinned float64 ndarrays) -> uis_predict() C ABI: H2D, cast+GEMM+beam kernels, D2H int32 labels -> Python lists'},
       'gpu_launches': int(args.steps * 2),
       'clocks': clocks,
-      'roofline': {'bound': 'hbm', 'kernel': 'uis_beam_kernel<512,256,12>', 'achieved': achieved, 'peak': peak,
-                   'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+      'roofline': {'bound': 'hbm', 'kernel': 'uis_beam_kernel<512,256>', 'achieved': achieved, 'peak': peak,
+                   'unit': 'GB/s', 'frac': achieved / peak, 'traffic': measured_traffic(U), 'peak_source': peak_src,
+                   'traffic_source': 'profiles/r1_traffic.json (ncu dram__bytes_read+write, same workload)',
                    'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': beam_avg_ms,
-                   'note': 'weights are L2-resident: "achieved" is the weight stream L2->SM plus HBM I/O, so frac>1 is possible; '
-                           'the binding unit is the fp32 FMA pipe, see fp32',
+                   'note': 'algorithmic bytes = SURVEY 8(d): weights streamed once per beam-step pass (4.72 MB, L2-resident, '
+                           'so this stream never reaches DRAM: traffic << algorithmic) + per-frame HBM I/O; the binding '
+                           'unit is the fp32 FMA pipe, see fp32',
                    'fp32': {'achieved_tflops': flops / (beam_avg_ms / 1e3) / 1e12, 'peak_tflops': fp32_peak,
                             'frac': flops / (beam_avg_ms / 1e3) / 1e12 / fp32_peak, 'sm_mhz_used': sm_mhz}},
       'kernel_stats': {k: st[k] for k in ('beam_steps', 'gru_columns', 'weight_passes', 'candidates', 'max_k', 'ctas')},
       'prepass_ms': float(np.mean(prepass_ms)),
   }
+  if world == 1 and not args.no_secondary:
+    out['secondary'] = secondary_metrics(model, torch)
   if not args.no_cpu_baseline:
     out['cpu_baseline'] = cpu_baseline_port()
   print(json.dumps(out), flush=True)
@@ -353,6 +420,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--utts', type=int, default=296, help='utterances per GPU per step')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-secondary', action='store_true', help='skip the config-3 / config-4 side measurements')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)
