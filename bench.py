@@ -135,6 +135,19 @@ def secondary_metrics(model, torch):
                                         'gru_columns_per_step': st3['gru_columns'] / max(1, st3['beam_steps'])}
   except Exception as err:  # pylint: disable=broad-except
     out['config3_beam30_lookahead2'] = {'error': str(err)[:200]}
+  try:  # latency mode (U=1) and a small batch (U=64), device-resident, same workload
+    from uisrnn_b200.synth import synth_utt
+    for U1 in (1, 64):
+      xs = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N_FRAMES, dim=DIM)[0] for u in range(U1)]).astype(np.float32)).cuda()
+      lab = torch.empty(U1 * N_FRAMES, dtype=torch.int32, device='cuda')
+      offs = np.arange(U1 + 1, dtype=np.int64) * N_FRAMES
+      for _ in range(2):
+        model.predict_device(xs.data_ptr(), offs, lab.data_ptr(), beam_size=BEAM, look_ahead=LOOK_AHEAD, test_iteration=TEST_ITER)
+        stu = model.stats()
+      out['config2_U%d' % U1] = {'frames_per_s': U1 * N_FRAMES / ((stu['beam_ms'] + stu['prepass_ms']) / 1e3),
+                                 'ms': stu['beam_ms'] + stu['prepass_ms'], 'ctas': stu['ctas'], 'lanes': stu['lanes']}
+  except Exception as err:  # pylint: disable=broad-except
+    out['config2_small_batches'] = {'error': str(err)[:200]}
   try:  # config 4: fit() iteration on 50k concatenated frames, batch_size=32 (device trainer, csrc/uis_train.cu)
     import random
     from uisrnn_b200 import native, utils
