@@ -118,54 +118,69 @@ __global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------
-// Recurrent products: C[b][n] (+)= sum_k A[b][k] * W[k][n]   for b < nb <= 32 (one time step).
-// Lane = output column n (coalesced W rows), 32 accumulators per thread (one per sequence), the
-// K dimension split over the 8 warps of the CTA and reduced through shared memory.  A is read with
-// warp-uniform 128-bit loads (L1 broadcast).  Grid = N / 32 CTAs.
-__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, int lda,
-                                                          const float* __restrict__ W, float* __restrict__ C,
-                                                          int ldc, int nb, int N, int K, int accumulate) {
-  __shared__ float part[8][32][33];
-  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
-  const int n = blockIdx.x * 32 + lane;
-  const int kslice = (K + 7) / 8;
-  const int k0 = w * kslice, k1 = min(K, k0 + kslice);
-  float acc[32];
+// Recurrent products of one time step:  C[b][n] (+)= sum_k A[b][k] * W[k][n],  b < nb <= 32.
+// The output is only 32 rows tall, so parallelism comes from the K dimension: grid = (N/64 column
+// tiles, kSplit K-slices).  Each CTA multiplies its 32 x 64 x (K/kSplit) slab with shared-memory
+// tiles (coalesced loads), parks the partial tile in global memory, and the LAST CTA to finish a
+// column tile (atomic ticket) adds the kSplit partials in a fixed order -- deterministic, one launch.
+constexpr int kSplit = 16;
+__global__ void __launch_bounds__(256) splitk_gemm_kernel(const float* __restrict__ A, int lda,
+                                                          const float* __restrict__ W, float* __restrict__ C, int ldc,
+                                                          int nb, int N, int K, int accumulate,
+                                                          float* __restrict__ partial, unsigned* __restrict__ tickets) {
+  __shared__ float As[16][32 + 1];
+  __shared__ float Ws[16][64 + 1];
+  __shared__ unsigned last_flag;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;  // micro-tile: rows ty*2.., cols tx*4..
+  const int n0 = blockIdx.x * 64, sp = blockIdx.y;
+  const int kslice = ((K + kSplit - 1) / kSplit + 15) / 16 * 16;
+  const int k0 = sp * kslice, k1 = min(K, k0 + kslice);
+  float acc[2][4] = {};
+  for (int kb = k0; kb < k1; kb += 16) {
+    for (int q = tid; q < 32 * 16; q += 256) {
+      const int kk = q % 16, b = q / 16;
+      As[kk][b] = (b < nb && kb + kk < k1) ? A[(size_t)b * lda + kb + kk] : 0.f;
+    }
+    for (int q = tid; q < 64 * 16; q += 256) {
+      const int nn = q % 64, kk = q / 64;
+      Ws[kk][nn] = (n0 + nn < N && kb + kk < k1) ? W[(size_t)(kb + kk) * N + n0 + nn] : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-  if (n < N) {
-    int k = k0;
-    for (; k + 4 <= k1; k += 4) {
-      const float w0 = W[(size_t)k * N + n], w1 = W[(size_t)(k + 1) * N + n];
-      const float w2 = W[(size_t)(k + 2) * N + n], w3 = W[(size_t)(k + 3) * N + n];
+    for (int kk = 0; kk < 16; ++kk) {
+      const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        if (b < nb) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * lda + k));
-          acc[b] = fmaf(a.x, w0, acc[b]); acc[b] = fmaf(a.y, w1, acc[b]);
-          acc[b] = fmaf(a.z, w2, acc[b]); acc[b] = fmaf(a.w, w3, acc[b]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float w = Ws[kk][tx * 4 + j];
+        acc[0][j] = fmaf(a0, w, acc[0][j]);
+        acc[1][j] = fmaf(a1, w, acc[1][j]);
       }
     }
-    for (; k < k1; ++k) {
-      const float w0 = W[(size_t)k * N + n];
-#pragma unroll
-      for (int b = 0; b < 32; ++b)
-        if (b < nb) acc[b] = fmaf(__ldg(A + (size_t)b * lda + k), w0, acc[b]);
-    }
+    __syncthreads();
   }
+  float* mine = partial + ((size_t)blockIdx.x * kSplit + sp) * (32 * 64);
 #pragma unroll
-  for (int b = 0; b < 32; ++b) part[w][b][lane] = acc[b];
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mine[(ty * 2 + i) * 64 + tx * 4 + j] = acc[i][j];
+  __threadfence();
   __syncthreads();
-  // thread (b = tid / 8 .., ) : 256 threads sum 32 x 32 outputs, 4 each
-  for (int q = threadIdx.x; q < 32 * 32; q += 256) {
-    const int b = q / 32, l = q % 32;
-    const int nn = blockIdx.x * 32 + l;
-    if (b < nb && nn < N) {
+  if (tid == 0) {
+    const unsigned t = atomicAdd(&tickets[blockIdx.x], 1u);
+    last_flag = (t == kSplit - 1) ? 1u : 0u;
+    if (last_flag) tickets[blockIdx.x] = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  const float* tile = partial + (size_t)blockIdx.x * kSplit * (32 * 64);
+  for (int q = tid; q < 32 * 64; q += 256) {
+    const int b = q / 64, nn = q % 64;
+    if (b < nb && n0 + nn < N) {
       float v = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) v += part[ww][b][l];
-      float* dst = C + (size_t)b * ldc + nn;
+      for (int s2 = 0; s2 < kSplit; ++s2) v += tile[(size_t)s2 * (32 * 64) + q];
+      float* dst = C + (size_t)b * ldc + n0 + nn;
       *dst = accumulate ? (*dst + v) : v;
     }
   }
@@ -402,7 +417,8 @@ struct uis_trainer {
   uis::DBuf params, grads, m, v, segbuf;  // segbuf: seg_off (as int bits) is separate below
   int* seg_off_d = nullptr;
   float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 16][g_sumsq 16]
-  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial;
+  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial, skpart;
+  unsigned* tickets = nullptr;
 };
 
 namespace {
@@ -439,6 +455,8 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
     CUT(cudaMalloc(&t->seg_off_d, sizeof(t->seg_off_h)));
     CUT(cudaMemcpy(t->seg_off_d, t->seg_off_h, sizeof(t->seg_off_h), cudaMemcpyHostToDevice));
     CUT(cudaMalloc(&t->small, (size_t)(2 * D + 64) * 4));
+    CUT(cudaMalloc(&t->tickets, 256 * sizeof(unsigned)));
+    CUT(cudaMemset(t->tickets, 0, 256 * sizeof(unsigned)));
     return 0;
   };
   if (int rc = body()) { uis_trainer_destroy(t); return rc; }
@@ -451,10 +469,11 @@ int uis_trainer_destroy(uis_trainer* t) {
   cudaSetDevice(t->device);
   uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
                        &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
-                       &t->partial};
+                       &t->partial, &t->skpart};
   for (auto* b : bufs) b->release();
   if (t->seg_off_d) cudaFree(t->seg_off_d);
   if (t->small) cudaFree(t->small);
+  if (t->tickets) cudaFree(t->tickets);
   delete t;
   return 0;
 }
@@ -495,6 +514,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   if (int rc = t->whh_t.ensure((size_t)3 * H * H)) return rc;
   if (int rc = t->ghbuf.ensure((size_t)32 * 3 * H)) return rc;
   if (int rc = t->partial.ensure((size_t)16 * kSumsqBlocks)) return rc;
+  if (int rc = t->skpart.ensure((size_t)((3 * H + 63) / 64) * kSplit * 32 * 64)) return rc;
+  if ((3 * H + 63) / 64 > 256) return api_fail(UIS_ERR_UNSUPPORTED, "hidden size too large for the training kernels");
   float* P = t->params.p;
   float* G = t->grads.p;
   const int* so = t->seg_off_h;
@@ -523,8 +544,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   for (int tt = 0; tt < L; ++tt) {
     if (nb[tt] == 0) break;
     const size_t o = (size_t)tt * B;
-    skinny_gemm_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H, nb[tt], 3 * H,
-                                                          H, 0);
+    splitk_gemm_kernel<<<dim3((3 * H + 63) / 64, kSplit), 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H,
+                                                                        nb[tt], 3 * H, H, 0, t->skpart.p, t->tickets);
     gru_gate_fwd_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, P + so[SEG_BHH], t->gi.p + o * 3 * H,
                                                                   t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
                                                                   t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, nb[tt], H);
@@ -554,8 +575,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
                                                                   t->hs.p + o * H, t->dgi.p + o * 3 * H,
                                                                   t->dgh.p + o * 3 * H, nb[tt], H);
     // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
-    skinny_gemm_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p, H, nb[tt], H,
-                                                      3 * H, 1);
+    splitk_gemm_kernel<<<dim3((H + 63) / 64, kSplit), 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p,
+                                                                    H, nb[tt], H, 3 * H, 1, t->skpart.p, t->tickets);
   }
   CUT(cudaGetLastError());
   if (int rc = gemm<true, false>(st, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
