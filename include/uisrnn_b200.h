@@ -173,12 +173,17 @@ int uis_trainer_destroy(uis_trainer* t);
  * [L][B][D] zero-padded, time-major, row 0 all zeros; lengths[B] (incl. the zero row) sorted
  * descending with lengths[0] == L; B <= 32.  mode 0: forward + backward + clip + Adam + clamp;
  * mode 1: forward + backward only (for gradient checks).  losses_out[3] (host, may be NULL) =
- * negative log likelihood, sigma2 prior, regularisation -- the three numbers uisrnn.py:297-310 logs. */
+ * negative log likelihood, sigma2 prior, regularisation -- the three numbers uisrnn.py:297-310 logs.
+ * With losses_out == NULL the call only enqueues work on `stream` (the host batch has been staged
+ * when it returns); read the losses later with uis_trainer_losses(). */
 int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
                      float* losses_out, void* stream);
 
 /* what = 0: current parameters, 1: gradients of the last step.  out: ten host pointers (NULL = skip). */
 int uis_trainer_get(uis_trainer* t, int what, float* const* out);
+
+/* Losses of the last `count` (<= 4096) steps, oldest first: out[count][3] host floats.  Synchronises. */
+int uis_trainer_losses(uis_trainer* t, int count, float* out);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,8 @@ for mode in ('native', 'torch'):
     for _ in range(iters):
       xi, li = utils.pack_batch(subs, lens, 32, 256)
       rows += int(li.sum())
-      tr.step(xi.astype(np.float32), li)
+      tr.step_async(xi.astype(np.float32), li)
+    tr.losses(1)
     dt = time.perf_counter() - t0
   else:
     t.train_iteration = iters

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -44,19 +45,25 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                    const float* __restrict__ bias, const float* __restrict__ mask,
                                                    float* __restrict__ C, int M, int N, int K, int relu,
-                                                   int accumulate) {
+                                                   int accumulate, float* __restrict__ partial,
+                                                   unsigned* __restrict__ tickets) {
   __shared__ float As[16][64 + 1];
   __shared__ float Bs[16][64 + 1];
+  __shared__ unsigned last_flag;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  // split-K over gridDim.z (weight-gradient products have K = #rows in the thousands but few tiles)
+  const int splits = gridDim.z;
+  const int kslice = ((K + splits - 1) / splits + 15) / 16 * 16;
+  const int kbeg = blockIdx.z * kslice, kend = min(K, kbeg + kslice);
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
     for (int q = tid; q < 64 * 16; q += 256) {
       int mm, kk;
       if (TA) { mm = q % 64; kk = q / 64; } else { kk = q % 16; mm = q / 16; }
       const int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
       As[kk][mm] = v;
     }
     for (int q = tid; q < 64 * 16; q += 256) {
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
       if (TB) { kk = q % 16; nn = q / 16; } else { nn = q % 64; kk = q / 64; }
       const int gn = n0 + nn, gk = k0 + kk;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
+      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -81,6 +88,33 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
+  }
+  if (splits > 1) {  // park the partial tile; the last CTA of this tile folds all of them in order
+    const unsigned tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = partial + ((size_t)tile_id * splits + blockIdx.z) * (64 * 64);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mine[(ty * 4 + i) * 64 + tx * 4 + j] = acc[i][j];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(&tickets[tile_id], 1u);
+      last_flag = (t == (unsigned)splits - 1) ? 1u : 0u;
+      if (last_flag) tickets[tile_id] = 0;
+    }
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    const float* tile = partial + (size_t)tile_id * splits * (64 * 64);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        for (int s2 = 0; s2 < splits; ++s2) v += tile[(size_t)s2 * (64 * 64) + (ty * 4 + i) * 64 + tx * 4 + j];
+        acc[i][j] = v;
+      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -396,12 +430,26 @@ struct DBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct SplitCtx {
+  float* partial = nullptr;     // [tiles][splits][64*64]
+  size_t partial_cap = 0;       // floats
+  unsigned* tile_tickets = nullptr;
+  int ticket_cap = 0;
+};
+
 template <bool TA, bool TB>
-int gemm(cudaStream_t st, const float* A, const float* B, const float* bias, const float* mask, float* C, int M, int N,
-         int K, bool relu = false, bool acc = false) {
+int gemm(cudaStream_t st, const SplitCtx& sc, const float* A, const float* B, const float* bias, const float* mask,
+         float* C, int M, int N, int K, bool relu = false, bool acc = false) {
   if (M <= 0 || N <= 0) return 0;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0);
+  dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  // fill the machine (~4 CTAs per SM) when the tile count is small and K is long
+  while (splits < 16 && tiles * splits < 592 && K / (splits * 2) >= 128) splits *= 2;
+  if (splits > 1 && ((size_t)tiles * splits * 4096 > sc.partial_cap || tiles > sc.ticket_cap)) splits = 1;
+  grid.z = splits;
+  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0, sc.partial,
+                                          sc.tile_tickets);
   CUT(cudaGetLastError());
   return 0;
 }
@@ -413,12 +461,21 @@ struct uis_trainer {
   uis_train_hparams hp{};
   int seg_off_h[11];
   int total = 0, rnn_end = 0, sigma_begin = 0;
-  long long step = 0;
+  long long step = 0, calls = 0;
   uis::DBuf params, grads, m, v, segbuf;  // segbuf: seg_off (as int bits) is separate below
   int* seg_off_d = nullptr;
   float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 16][g_sumsq 16]
   uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial, skpart;
   unsigned* tickets = nullptr;
+  uis::SplitCtx sc;
+  uis::DBuf gemm_partial, loss_hist;
+  unsigned* gemm_tickets = nullptr;
+  long long hist_cap = 0;
+  // pinned staging for the batch (two buffers in flight) so that steps are truly asynchronous
+  float* pin[2] = {nullptr, nullptr};
+  size_t pin_cap = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  int pin_idx = 0;
 };
 
 namespace {
@@ -457,6 +514,10 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
     CUT(cudaMalloc(&t->small, (size_t)(2 * D + 64) * 4));
     CUT(cudaMalloc(&t->tickets, 256 * sizeof(unsigned)));
     CUT(cudaMemset(t->tickets, 0, 256 * sizeof(unsigned)));
+    CUT(cudaMalloc(&t->gemm_tickets, 4096 * sizeof(unsigned)));
+    CUT(cudaMemset(t->gemm_tickets, 0, 4096 * sizeof(unsigned)));
+    if (int rc = t->gemm_partial.ensure((size_t)1024 * 4096)) return rc;  // 16 MB of split-K partial tiles
+    t->sc.partial = t->gemm_partial.p; t->sc.partial_cap = t->gemm_partial.cap; t->sc.tile_tickets = t->gemm_tickets; t->sc.ticket_cap = 4096;
     return 0;
   };
   if (int rc = body()) { uis_trainer_destroy(t); return rc; }
@@ -469,11 +530,16 @@ int uis_trainer_destroy(uis_trainer* t) {
   cudaSetDevice(t->device);
   uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
                        &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
-                       &t->partial, &t->skpart};
+                       &t->partial, &t->skpart, &t->gemm_partial, &t->loss_hist};
   for (auto* b : bufs) b->release();
   if (t->seg_off_d) cudaFree(t->seg_off_d);
   if (t->small) cudaFree(t->small);
   if (t->tickets) cudaFree(t->tickets);
+  if (t->gemm_tickets) cudaFree(t->gemm_tickets);
+  for (int i = 0; i < 2; ++i) {
+    if (t->pin[i]) cudaFreeHost(t->pin[i]);
+    if (t->pin_ev[i]) cudaEventDestroy(t->pin_ev[i]);
+  }
   delete t;
   return 0;
 }
@@ -524,7 +590,25 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   std::vector<int> nb(L);
   for (int tt = 0; tt < L; ++tt) { int c = 0; while (c < B && lengths[c] > tt) ++c; nb[tt] = c; }
 
-  CUT(cudaMemcpyAsync(t->x.p, x_host, R * D * 4, cudaMemcpyHostToDevice, st));
+  {  // stage the batch in pinned memory: the H2D copy then overlaps the previous iteration's kernels
+    const size_t bytes = R * D * 4;
+    if (bytes > t->pin_cap) {
+      for (int i = 0; i < 2; ++i) {
+        if (t->pin_ev[i]) CUT(cudaEventSynchronize(t->pin_ev[i]));
+        if (t->pin[i]) cudaFreeHost(t->pin[i]);
+        t->pin[i] = nullptr;
+        CUT(cudaMallocHost(&t->pin[i], bytes + bytes / 4));
+        if (!t->pin_ev[i]) CUT(cudaEventCreateWithFlags(&t->pin_ev[i], cudaEventDisableTiming));
+      }
+      t->pin_cap = bytes + bytes / 4;
+    }
+    const int pi = t->pin_idx;
+    t->pin_idx ^= 1;
+    CUT(cudaEventSynchronize(t->pin_ev[pi]));  // the copy that last used this buffer has finished
+    std::memcpy(t->pin[pi], x_host, bytes);
+    CUT(cudaMemcpyAsync(t->x.p, t->pin[pi], bytes, cudaMemcpyHostToDevice, st));
+    CUT(cudaEventRecord(t->pin_ev[pi], st));
+  }
   CUT(cudaMemsetAsync(t->hs.p, 0, (R + B) * H * 4, st));
   CUT(cudaMemsetAsync(t->small, 0, (size_t)(2 * D + 64) * 4, st));
   CUT(cudaMemsetAsync(G, 0, (size_t)t->total * 4, st));
@@ -536,7 +620,7 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
     CUT(cudaMemcpyAsync(t->hs.p + (size_t)b * H, P + so[SEG_H0], (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
 
   // ---- forward
-  if (int rc = gemm<false, true>(st, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
+  if (int rc = gemm<false, true>(st, t->sc, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
   {  // k-major copy of W_hh for the recurrent products (the weights change every iteration)
     dim3 tg((H + 31) / 32, (3 * H + 31) / 32), tb(32, 8);
     transpose_kernel<<<tg, tb, 0, st>>>(P + so[SEG_WHH], t->whh_t.p, 3 * H, H);
@@ -552,8 +636,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   }
   CUT(cudaGetLastError());
   const float* out = t->hs.p + (size_t)B * H;  // out[t] = h_t ; padded rows stay zero
-  if (int rc = gemm<false, true>(st, out, P + so[SEG_W1], P + so[SEG_B1], nullptr, t->a1.p, (int)R, H, H, true)) return rc;
-  if (int rc = gemm<false, true>(st, t->a1.p, P + so[SEG_W2], P + so[SEG_B2], nullptr, t->mu.p, (int)R, D, H)) return rc;
+  if (int rc = gemm<false, true>(st, t->sc, out, P + so[SEG_W1], P + so[SEG_B1], nullptr, t->a1.p, (int)R, H, H, true)) return rc;
+  if (int rc = gemm<false, true>(st, t->sc, t->a1.p, P + so[SEG_W2], P + so[SEG_B2], nullptr, t->mu.p, (int)R, D, H)) return rc;
   const int bd_blocks = (B * D + 255) / 256;
   loss_fwd_kernel<<<bd_blocks, 256, 0, st>>>(t->mu.p, t->x.p, t->diff.p, sum_sq_d, cnt_d, nz, L, B, D);
   loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
@@ -561,12 +645,12 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   // ---- backward
   loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[SEG_SIGMA2], nz, t->dmu.p, L, B, D);
   CUT(cudaGetLastError());
-  if (int rc = gemm<true, false>(st, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[SEG_W2], D, H, (int)R)) return rc;
+  if (int rc = gemm<true, false>(st, t->sc, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[SEG_W2], D, H, (int)R)) return rc;
   colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(t->dmu.p, G + so[SEG_B2], (int)R, D);
-  if (int rc = gemm<false, false>(st, t->dmu.p, P + so[SEG_W2], nullptr, t->a1.p, t->dz1.p, (int)R, H, D)) return rc;  // * relu'
-  if (int rc = gemm<true, false>(st, t->dz1.p, out, nullptr, nullptr, G + so[SEG_W1], H, H, (int)R)) return rc;
+  if (int rc = gemm<false, false>(st, t->sc, t->dmu.p, P + so[SEG_W2], nullptr, t->a1.p, t->dz1.p, (int)R, H, D)) return rc;  // * relu'
+  if (int rc = gemm<true, false>(st, t->sc, t->dz1.p, out, nullptr, nullptr, G + so[SEG_W1], H, H, (int)R)) return rc;
   colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dz1.p, G + so[SEG_B1], (int)R, H);
-  if (int rc = gemm<false, false>(st, t->dz1.p, P + so[SEG_W1], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
+  if (int rc = gemm<false, false>(st, t->sc, t->dz1.p, P + so[SEG_W1], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
   for (int tt = L - 1; tt >= 0; --tt) {
     if (nb[tt] == 0) continue;
     const size_t o = (size_t)tt * B;
@@ -579,8 +663,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
                                                                     H, nb[tt], H, 3 * H, 1, t->skpart.p, t->tickets);
   }
   CUT(cudaGetLastError());
-  if (int rc = gemm<true, false>(st, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
-  if (int rc = gemm<true, false>(st, t->dgh.p, t->hs.p, nullptr, nullptr, G + so[SEG_WHH], 3 * H, H, (int)R)) return rc;
+  if (int rc = gemm<true, false>(st, t->sc, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
+  if (int rc = gemm<true, false>(st, t->sc, t->dgh.p, t->hs.p, nullptr, nullptr, G + so[SEG_WHH], 3 * H, H, (int)R)) return rc;
   colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgi.p, G + so[SEG_BIH], (int)R, 3 * H);
   colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[SEG_BHH], (int)R, 3 * H);
   colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[SEG_H0], B, H);  // d h0 = sum_b d h_{-1}
@@ -606,9 +690,29 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
                                                         (float)std::sqrt(bc2), t->hp.train_sigma2);
     CUT(cudaGetLastError());
   }
+  // loss history on the device: slot (calls mod capacity); losses_out == NULL => fully asynchronous step
+  if (!t->loss_hist.p) {
+    if (int rc = t->loss_hist.ensure(3 * 4096)) return rc;
+    t->hist_cap = 4096;
+  }
+  CUT(cudaMemcpyAsync(t->loss_hist.p + 3 * (t->calls % t->hist_cap), scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  t->calls += 1;
   if (losses_out) {
     CUT(cudaMemcpyAsync(losses_out, scalars, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUT(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// Losses of the last `count` (<= 4096) calls to uis_trainer_step, oldest first: out[count][3] (host).  Synchronises.
+int uis_trainer_losses(uis_trainer* t, int count, float* out) {
+  if (!t || !out || count < 0) return uis::api_fail(UIS_ERR_INVALID, "bad argument");
+  if (count > t->calls || count > t->hist_cap) return uis::api_fail(UIS_ERR_INVALID, "only %lld steps recorded", t->calls);
+  CUT(cudaSetDevice(t->device));
+  CUT(cudaDeviceSynchronize());
+  for (int i = 0; i < count; ++i) {
+    const long long slot = (t->calls - count + i) % t->hist_cap;
+    CUT(cudaMemcpy(out + 3 * i, t->loss_hist.p + 3 * slot, 3 * sizeof(float), cudaMemcpyDeviceToHost));
   }
   return 0;
 }

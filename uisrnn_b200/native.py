@@ -57,7 +57,7 @@ class Stats(C.Structure):
 EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destroy',
            'uis_model_constants', 'uis_predict', 'uis_predict_device',
            'uis_predict_workspace_bytes', 'uis_get_stats', 'uis_trainer_create',
-           'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get')
+           'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get', 'uis_trainer_losses')
 
 
 class TrainHParams(C.Structure):
@@ -116,6 +116,8 @@ def load_library():
                                    fp, C.c_void_p]
   lib.uis_trainer_get.restype = C.c_int
   lib.uis_trainer_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+  lib.uis_trainer_losses.restype = C.c_int
+  lib.uis_trainer_losses.argtypes = [C.c_void_p, C.c_int, fp]
   del ip
   _lib = lib
   return lib
@@ -282,6 +284,23 @@ class NativeTrainer:
       self.close()
     except Exception:  # pylint: disable=broad-except
       pass
+
+  def losses(self, count):
+    """(count, 3) array: losses of the last `count` steps, oldest first (synchronises)."""
+    out = np.zeros((count, 3), np.float32)
+    if count:
+      _check(self._lib, self._lib.uis_trainer_losses(self._h, count, out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+  def step_async(self, rnn_input, lengths, stream=0):
+    """Enqueues one full iteration and returns immediately (losses via `losses()`)."""
+    x = _f32(rnn_input)
+    L, B, D = x.shape
+    assert D == self.D
+    lens = np.ascontiguousarray(lengths, dtype=np.int32)
+    _check(self._lib, self._lib.uis_trainer_step(self._h, x.ctypes.data_as(C.c_void_p),
+                                                  lens.ctypes.data_as(C.POINTER(C.c_int32)), B, L, 0, None,
+                                                  C.c_void_p(stream)))
 
   def step(self, rnn_input, lengths, grads_only=False, stream=0):
     """rnn_input: float32 [L, B, D] zero-padded time-major batch; lengths: [B] descending.

@@ -237,15 +237,23 @@ class UISRNN:
     trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
     self.last_training_losses = []
     try:
+      pending = 0  # steps enqueued since the losses were last read back
       for num_iter in range(args.train_iteration):
+        # the device works on iteration i while the host packs the batch of iteration i + 1
         rnn_input, lengths = utils.pack_batch(sub_sequences, seq_lengths, args.batch_size, self.observation_dim)
-        loss1, loss2, loss3 = trainer.step(rnn_input.astype(np.float32), lengths)
-        self.last_training_losses.append(loss1)
-        if num_iter % 10 == 0 or num_iter == args.train_iteration - 1:
-          self.logger.print(
-              2, 'Iter: {:d}  \tTraining Loss: {:.4f}    \n    Negative Log Likelihood: {:.4f}\t'
-                 'Sigma2 Prior: {:.4f}\tRegularization: {:.4f}'.format(
-                     num_iter, loss1 + loss2 + loss3, loss1, loss2, loss3))
+        trainer.step_async(rnn_input.astype(np.float32), lengths)
+        pending += 1
+        log_now = num_iter % 10 == 0 or num_iter == args.train_iteration - 1
+        if log_now or pending == 4096:
+          recent = trainer.losses(pending)
+          self.last_training_losses.extend(float(v) for v in recent[:, 0])
+          pending = 0
+          if log_now:
+            loss1, loss2, loss3 = (float(v) for v in recent[-1])
+            self.logger.print(
+                2, 'Iter: {:d}  \tTraining Loss: {:.4f}    \n    Negative Log Likelihood: {:.4f}\t'
+                   'Sigma2 Prior: {:.4f}\tRegularization: {:.4f}'.format(
+                       num_iter, loss1 + loss2 + loss3, loss1, loss2, loss3))
       trained = trainer.parameters()
     finally:
       trainer.close()
