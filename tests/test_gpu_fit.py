@@ -88,6 +88,23 @@ def test_losses_and_gradients_match_autograd():
     assert _rel(got[name].reshape(want[name].shape), want[name]) < 2e-3, name
 
 
+def test_gradients_at_default_model_size_batch32():
+  """BASELINE config 4 shape: D=256, H=512, batch_size=32."""
+  from uisrnn_b200 import utils
+  model, targs, subs, lens = _model_and_data(D=256, H=512, seed=21)
+  targs.batch_size = 32
+  model.rnn_model.train()
+  rnn_input, lengths = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+  want_losses, want = _torch_losses_and_grads(model, targs, rnn_input, lengths)
+  trainer = _native_trainer(model, targs)
+  got_losses = trainer.step(rnn_input.astype(np.float32), lengths, grads_only=True)
+  got = trainer.gradients()
+  for a, b in zip(got_losses, want_losses):
+    assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (got_losses, want_losses)
+  for name in want:
+    assert _rel(got[name].reshape(want[name].shape), want[name]) < 2e-3, name
+
+
 def test_one_adam_step_matches_torch():
   import torch
   from torch import nn
