@@ -67,7 +67,7 @@ typedef struct uis_debug_taps {
   float* final_scores;     /* [U][beam_size] final neg_likelihood per hypothesis (+inf pad)    */
   int32_t* final_k;        /* [U] clusters in the best hypothesis                              */
   float* best_mean;        /* [kcap][D]  mean_set   of the best hypothesis of `trace_utt`      */
-  float* best_hidden;      /* [kcap][H]  hidden_set of the best hypothesis of `trace_utt`      */
+  float* best_hidden;      /* [kcap][depth][H] hidden_set of the best hypothesis of `trace_utt` */
   int32_t* best_blocks;    /* [kcap]     block_counts of the best hypothesis of `trace_utt`    */
 } uis_debug_taps;
 
@@ -99,10 +99,11 @@ const char* uis_last_error(void);
  * takes the CoreRNN parameters (uisrnn.py:35-43, PyTorch state_dict layout, row-major fp32):
  *   w_ih [3H,D]  w_hh [3H,H]  b_ih [3H]  b_hh [3H]   (gru.*_l0, gate order r,z,n)
  *   w1 [H,H] b1 [H] (linear_mean1)   w2 [D,H] b2 [D] (linear_mean2)
- *   h0 [H] (rnn_init_hidden)   sigma2 [D]
+ *   h0 [depth,H] (rnn_init_hidden)   sigma2 [D]
+ * Stacked layers (depth 2..4): w_ih = [gru.weight_ih_l0 (3H x D) | gru.weight_ih_l1 (3H x H) | ...]
+ * concatenated, w_hh / b_ih / b_hh = the per-layer tensors concatenated in layer order.
  * Pointers may be host or device memory (copied, never retained).  Precomputes the per-model
  * constants CoreRNN(zeros, rnn_init_hidden) that uisrnn.py:435-439 recomputes per candidate.
- * depth must be 1 (UIS_ERR_UNSUPPORTED otherwise).
  */
 int uis_model_create(uis_model** out, int device, int D, int H, int depth,
                      const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -111,7 +112,7 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth,
                      double crp_alpha);
 int uis_model_destroy(uis_model* m);
 
-/* Copies the per-model constants back (host buffers, fp32): mean0 [D], hidden0 [H]. */
+/* Copies the per-model constants back (host buffers, fp32): mean0 [D], hidden0 [depth][H]. */
 int uis_model_constants(uis_model* m, float* mean0, float* hidden0);
 
 /*

@@ -18,6 +18,7 @@ Fixtures written (all float32 where the reference computes in float32):
   toy_trace.npz      per-step trace of toy utterances 0 and 1
   synth500.npz       two 500-frame synthetic utterances (seeds 1000, 1001): reference labels
   model_small.npz    D=64,H=128 model trained by the reference on synthetic data
+  model_small_d2.npz, depth2_cases.npz   the same with rnn_depth=2
   small_cases.npz    small-model cases: beam/look_ahead/test_iteration variants, traces
 Usage:  python oracle/make_golden.py [--only NAME] [--jobs 8]
 """
@@ -297,6 +298,37 @@ def make_small_cases(jobs):
   np.savez_compressed(os.path.join(GOLD, 'small_cases.npz'), **o)
 
 
+def make_model_small_d2():
+  """Depth-2 GRU (nn.GRU with inter-layer dropout in training), D=64, H=128."""
+  seed_all(9)
+  m, t, _ = ref_args(observation_dim=64, rnn_hidden_size=128, rnn_depth=2, train_iteration=300,
+                     learning_rate=2e-3, batch_size=16)
+  seqs, ids = synth.synth_training_set(5200, 80, n_frames=80, dim=64, n_spk=3, noise=0.08)
+  model = ref.UISRNN(m)
+  model.fit(seqs, ids, t)
+  np.savez(os.path.join(GOLD, 'model_small_d2.npz'), **model_to_dict(model))
+
+
+DEPTH2_CASES = [
+    ('d2_b10', 6101, 70, 3, dict(beam_size=10, look_ahead=1, test_iteration=2)),
+    ('d2_la2', 6102, 33, 3, dict(beam_size=5, look_ahead=2, test_iteration=1)),
+]
+
+
+def make_depth2_cases(jobs):
+  d = dict(np.load(os.path.join(GOLD, 'model_small_d2.npz')))
+  seqs = [synth.synth_utt(s, n_frames=n, dim=64, n_spk=k, noise=0.08)[0] for (_, s, n, k, _) in DEPTH2_CASES]
+  trs = pmap(_trace_worker, [(d, x, kw) for x, (_, _, _, _, kw) in zip(seqs, DEPTH2_CASES)], jobs)
+  o = {'names': np.array([c[0] for c in DEPTH2_CASES])}
+  for (name, seed, n, k, kw), x, tr in zip(DEPTH2_CASES, seqs, trs):
+    o[name + '_x'] = x.astype(np.float32)
+    o[name + '_args'] = np.array([kw['beam_size'], kw['look_ahead'], kw['test_iteration']])
+    for key, v in tr.items():
+      o['{}_{}'.format(name, key)] = v
+    print(name, 'labels', tr['labels'][:40])
+  np.savez_compressed(os.path.join(GOLD, 'depth2_cases.npz'), **o)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--only', default=None)
@@ -305,7 +337,8 @@ def main():
   os.makedirs(GOLD, exist_ok=True)
   steps = [('model_toy100', make_model_toy100), ('toy_test', lambda: make_toy_test(a.jobs)),
            ('synth500', lambda: make_synth500(a.jobs)), ('model_small', make_model_small),
-           ('small_cases', lambda: make_small_cases(a.jobs))]
+           ('small_cases', lambda: make_small_cases(a.jobs)), ('model_small_d2', make_model_small_d2),
+           ('depth2_cases', lambda: make_depth2_cases(a.jobs))]
   for name, fn in steps:
     if a.only and name not in a.only.split(','):
       continue

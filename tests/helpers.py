@@ -26,8 +26,12 @@ def toy_utterances():
   return xs, labs
 
 
-def small_cases():
-  g = np.load(os.path.join(GOLDEN, 'small_cases.npz'))
+def depth2_cases():
+  return small_cases('depth2_cases.npz')
+
+
+def small_cases(fixture='small_cases.npz'):
+  g = np.load(os.path.join(GOLDEN, fixture))
   out = []
   for name in g['names']:
     name = str(name)

@@ -61,11 +61,23 @@ def test_unsupported_configurations_raise_instead_of_falling_back():
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   import uisrnn
   m, _, _ = uisrnn.parse_arguments([])
-  m.rnn_depth, m.rnn_hidden_size, m.observation_dim, m.transition_bias, m.verbosity = 2, 128, 64, 0.1, 0
+  m.rnn_depth, m.rnn_hidden_size, m.observation_dim, m.transition_bias, m.verbosity = 5, 128, 64, 0.1, 0
   deep = uisrnn.UISRNN(m)
   with pytest.raises(native.NativeError) as ei:
-    deep.predict(np.random.rand(5, 64), inference_args())       # depth 2: no kernel
+    deep.predict(np.random.rand(5, 64), inference_args())       # depth 5 > 4: no kernel
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
+  m.rnn_hidden_size = 96                                         # no kernel instantiated for H=96
+  odd = uisrnn.UISRNN(m)
+  with pytest.raises(native.NativeError):
+    odd.predict(np.random.rand(5, 64), inference_args())
+
+
+def test_depth2_model_through_the_api():
+  from helpers import depth2_cases
+  model = uisrnn_from_weights(load_weights('model_small_d2.npz'), enable_cuda=True)
+  for case in depth2_cases():
+    args = inference_args(case['beam_size'], case['look_ahead'], case['test_iteration'])
+    assert model.predict(case['x'], args) == case['labels'].tolist()
 
 
 def test_cluster_table_overflow_is_retried_with_larger_tables(monkeypatch):

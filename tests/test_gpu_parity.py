@@ -5,7 +5,7 @@ running means within 1e-5 absolute."""
 import numpy as np
 import pytest
 
-from helpers import (GOLDEN, compare_trace, load_weights, oracle_model, rel_err, small_cases,
+from helpers import (GOLDEN, compare_trace, depth2_cases, load_weights, oracle_model, rel_err, small_cases,
                      toy_utterances, uis_oracle)
 
 pytestmark = pytest.mark.gpu
@@ -36,7 +36,7 @@ def test_model_constants_match_oracle(small_model, toy_model):
     om = oracle_model(name)
     mean0, hidden0 = nm.constants()
     assert np.max(np.abs(mean0 - om.mean0)) < STATE_ATOL
-    assert np.max(np.abs(hidden0 - om.hidden0[0])) < STATE_ATOL
+    assert np.max(np.abs(hidden0 - om.hidden0)) < STATE_ATOL
 
 
 @pytest.mark.parametrize('case', small_cases(), ids=lambda c: c['name'])
@@ -52,7 +52,7 @@ def test_small_cases_match_reference_golden(small_model, case):
   nb = len(case['final_scores'])
   assert rel_err(dbg['final_scores'][0][:nb], case['final_scores']) < SCORE_RTOL
   assert np.all(np.isinf(dbg['final_scores'][0][nb:]))
-  assert np.max(np.abs(dbg['best_hidden'] - case['final_hidden'][:, 0, :])) < STATE_ATOL
+  assert np.max(np.abs(dbg['best_hidden'] - case['final_hidden'])) < STATE_ATOL
   assert np.max(np.abs(dbg['best_mean'] - case['final_mean'])) < STATE_ATOL
   assert np.array_equal(dbg['best_blocks'], case['final_blocks'])
 
@@ -74,7 +74,7 @@ def test_toy_trace_matches_reference(toy_model, idx):
   _, dbg = toy_model.predict([xs[idx]], trace_utt=0)
   compare_trace(dbg['win'], dbg['score'], dbg['off'], g['u%d_win' % idx], g['u%d_score' % idx],
                 g['u%d_off' % idx], rtol=SCORE_RTOL)
-  assert np.max(np.abs(dbg['best_hidden'] - g['u%d_final_hidden' % idx][:, 0, :])) < STATE_ATOL
+  assert np.max(np.abs(dbg['best_hidden'] - g['u%d_final_hidden' % idx])) < STATE_ATOL
   assert np.max(np.abs(dbg['best_mean'] - g['u%d_final_mean' % idx])) < STATE_ATOL
 
 
@@ -207,3 +207,33 @@ def test_test_iteration_is_tiling_full_size(toy_model):
   twice = toy_model.predict([np.concatenate([x, x])], test_iteration=1)[0]
   tiled = toy_model.predict([x], test_iteration=2)[0]
   assert tiled.tolist() == twice[700:].tolist()
+
+
+@pytest.mark.parametrize('case', depth2_cases(), ids=lambda c: c['name'])
+def test_depth2_matches_reference_golden(native, case):
+  """Stacked GRU (rnn_depth=2): labels, per-step winners and both layers' hidden states against the
+  unmodified reference (look_ahead 1 and 2)."""
+  model = native.NativeModel(load_weights('model_small_d2.npz'))
+  labs, dbg = model.predict([case['x']], beam_size=case['beam_size'], look_ahead=case['look_ahead'],
+                            test_iteration=case['test_iteration'], trace_utt=0)
+  assert labs[0].tolist() == case['labels'].tolist()
+  compare_trace(dbg['win'], dbg['score'], dbg['off'], case['win'], case['score'], case['off'], rtol=SCORE_RTOL)
+  assert dbg['best_hidden'].shape == case['final_hidden'].shape
+  assert np.max(np.abs(dbg['best_hidden'] - case['final_hidden'])) < STATE_ATOL
+  assert np.max(np.abs(dbg['best_mean'] - case['final_mean'])) < STATE_ATOL
+
+
+def test_depth3_untrained_matches_oracle(native):
+  rng = np.random.default_rng(3)
+  H, D, depth = 128, 64, 3
+  u = lambda *s: (rng.uniform(-1, 1, size=s) / np.sqrt(H)).astype(np.float32)
+  w = {'depth': depth, 'w1': u(H, H), 'b1': u(H), 'w2': u(D, H), 'b2': u(D), 'h0': u(depth, 1, H),
+       'sigma2': (0.05 + 0.1 * rng.random(D)).astype(np.float32), 'transition_bias': 0.15, 'crp_alpha': 1.0}
+  for l in range(depth):
+    w['weight_ih_l%d' % l] = u(3 * H, D if l == 0 else H); w['weight_hh_l%d' % l] = u(3 * H, H)
+    w['bias_ih_l%d' % l] = u(3 * H); w['bias_hh_l%d' % l] = u(3 * H)
+  model = native.NativeModel(w)
+  om = uis_oracle.OracleModel(w)
+  x = rng.standard_normal((21, D)) * 0.3
+  got = model.predict([x], beam_size=6, test_iteration=2, kcap=64)[0]
+  assert got.tolist() == uis_oracle.predict_single(om, x, beam_size=6, look_ahead=1, test_iteration=2)

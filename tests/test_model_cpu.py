@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import uisrnn
-from helpers import inference_args, load_weights, small_cases, toy_utterances, uisrnn_from_weights
+from helpers import depth2_cases, inference_args, load_weights, small_cases, toy_utterances, uisrnn_from_weights
 
 
 def _tiny_args():
@@ -136,6 +136,13 @@ def test_four_clusters_depth2_end_to_end(tmp_path):
 def test_cpu_decoder_matches_reference_golden(case):
   """beam_cpu.py (any look_ahead) against labels produced by the unmodified reference."""
   model = uisrnn_from_weights(load_weights('model_small.npz'))
+  args = inference_args(case['beam_size'], case['look_ahead'], case['test_iteration'])
+  assert model.predict(case['x'], args) == case['labels'].tolist()
+
+
+@pytest.mark.parametrize('case', depth2_cases(), ids=lambda c: c['name'])
+def test_cpu_decoder_depth2_matches_reference_golden(case):
+  model = uisrnn_from_weights(load_weights('model_small_d2.npz'))
   args = inference_args(case['beam_size'], case['look_ahead'], case['test_iteration'])
   assert model.predict(case['x'], args) == case['labels'].tolist()
 

@@ -3,7 +3,7 @@ unmodified reference (oracle/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from helpers import load_weights, oracle_model, rel_err, small_cases, toy_utterances, uis_oracle, GOLDEN
+from helpers import depth2_cases, load_weights, oracle_model, rel_err, small_cases, toy_utterances, uis_oracle, GOLDEN
 
 SCORE_RTOL = 1e-5   # scores within 1e-5 relative
 STATE_ATOL = 1e-5   # GRU hidden / mean within 1e-5 abs
@@ -26,6 +26,20 @@ def test_small_cases_match_reference(case):
   assert np.max(np.abs(rec['final_mean'] - case['final_mean'])) < STATE_ATOL
   assert np.array_equal(rec['final_blocks'], case['final_blocks'])
   assert np.array_equal(rec['full_trace'], case['full_trace'])
+
+
+@pytest.mark.parametrize('case', depth2_cases(), ids=lambda c: c['name'])
+def test_depth2_cases_match_reference(case):
+  """Pins the oracle's stacked-GRU path (rnn_depth=2) to the unmodified reference."""
+  m = oracle_model('model_small_d2.npz')
+  rec = {}
+  lab = uis_oracle.predict_single(m, case['x'], beam_size=case['beam_size'], look_ahead=case['look_ahead'],
+                                  test_iteration=case['test_iteration'], record=rec)
+  assert lab == case['labels'].tolist()
+  assert np.array_equal(rec['win'], case['win'])
+  assert rel_err(rec['score'], case['score']) < SCORE_RTOL
+  assert np.max(np.abs(rec['final_hidden'] - case['final_hidden'])) < STATE_ATOL
+  assert np.max(np.abs(rec['final_mean'] - case['final_mean'])) < STATE_ATOL
 
 
 def test_per_model_constants_match_torch_free_formula():

@@ -81,10 +81,11 @@ struct DevBuf {
 }  // namespace
 
 struct uis_model {
-  int device = 0, D = 0, H = 0, num_sms = 0;
+  int device = 0, D = 0, H = 0, depth = 1, num_sms = 0;
   double p0 = 0, alpha = 0;
   // weights, k-major
   DevBuf wih_t, whh_t, w1_t, w2_t, bih, bhh, b1, b2, wvec, mean0, hidden0;
+  DevBuf wih_up_t;  // [depth-1][H][3H]; whh_t is [depth][H][3H]; bih / bhh are [depth][3H]
   // log tables
   DevBuf logn, logtot;
   int log_cap = 0;
@@ -256,7 +257,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
 size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
   size_t b = 0;
   b += (size_t)pl.rows * 3 * m->H * 4;                                  // gi
-  b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->H) * 4;               // slot pools
+  b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->depth * m->H) * 4;    // slot pools
   b += (size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B * 4;  // back-pointers
   b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
   return b;
@@ -293,7 +294,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (int rc = m->queue_stats.ensure(32 * sizeof(unsigned long long))) return rc;
   if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
   if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.G * pl.P * D * sizeof(float))) return rc;
-  if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * H * sizeof(float))) return rc;
+  if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * m->depth * H * sizeof(float))) return rc;
   if (int rc = m->bp.ensure((size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B *
                             sizeof(unsigned)))
     return rc;
@@ -305,6 +306,13 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 
   uis::BeamParams p{};
   p.whh_t = m->whh_t.as<float>(); p.w1_t = m->w1_t.as<float>(); p.w2_t = m->w2_t.as<float>();
+  p.depth = m->depth;
+  for (int l = 1; l < m->depth; ++l) {
+    p.wih_up_t[l - 1] = m->wih_up_t.as<float>() + (size_t)(l - 1) * H * 3 * H;
+    p.whh_up_t[l - 1] = m->whh_t.as<float>() + (size_t)l * H * 3 * H;
+  }
+  p.bih_up = m->bih.as<float>() + 3 * H;   // layers >= 1
+  p.bhh_up = m->bhh.as<float>() + 3 * H;
   p.bhh = m->bhh.as<float>(); p.b1 = m->b1.as<float>(); p.b2 = m->b2.as<float>();
   p.wvec = m->wvec.as<float>(); p.mean0 = m->mean0.as<float>(); p.hidden0 = m->hidden0.as<float>();
   p.log_p0 = std::log(m->p0);          // np.log(self.transition_bias)      uisrnn.py:418
@@ -344,7 +352,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
       }
       if (taps->best_mean) {
         if (int rc = m->dbg_best_mean.ensure((size_t)pl.Kcap * D * 4)) return rc;
-        if (int rc = m->dbg_best_hidden.ensure((size_t)pl.Kcap * H * 4)) return rc;
+        if (int rc = m->dbg_best_hidden.ensure((size_t)pl.Kcap * m->depth * H * 4)) return rc;
         if (int rc = m->dbg_best_blocks.ensure((size_t)pl.Kcap * 4)) return rc;
         p.dbg_best_mean = m->dbg_best_mean.as<float>(); p.dbg_best_hidden = m->dbg_best_hidden.as<float>();
         p.dbg_best_blocks = m->dbg_best_blocks.as<int>();
@@ -384,7 +392,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
     if (p.dbg_best_mean) {
       CU(cudaMemcpy(taps->best_mean, p.dbg_best_mean, (size_t)pl.Kcap * D * 4, cudaMemcpyDeviceToHost));
       if (taps->best_hidden)
-        CU(cudaMemcpy(taps->best_hidden, p.dbg_best_hidden, (size_t)pl.Kcap * H * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(taps->best_hidden, p.dbg_best_hidden, (size_t)pl.Kcap * m->depth * H * 4, cudaMemcpyDeviceToHost));
       if (taps->best_blocks)
         CU(cudaMemcpy(taps->best_blocks, p.dbg_best_blocks, (size_t)pl.Kcap * 4, cudaMemcpyDeviceToHost));
     }
@@ -439,7 +447,8 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
   *out = nullptr;
   if (!w_ih || !w_hh || !b_ih || !b_hh || !w1 || !b1 || !w2 || !b2 || !h0 || !sigma2)
     return fail(UIS_ERR_INVALID, "NULL weight pointer");
-  if (depth != 1) return fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the sm_100a kernel implements depth 1 only", depth);
+  if (depth < 1 || depth > uis::kMaxDepth)
+    return fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the sm_100a kernels support 1..%d stacked GRU layers", depth, uis::kMaxDepth);
   if (!shape_supported(H, D))
     return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
   if (!(transition_bias > 0.0 && transition_bias < 1.0))
@@ -447,24 +456,47 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
   if (!(crp_alpha > 0.0)) return fail(UIS_ERR_INVALID, "crp_alpha must be > 0");
   CU(cudaSetDevice(device));
   uis_model* m = new uis_model();
-  m->device = device; m->D = D; m->H = H; m->p0 = transition_bias; m->alpha = crp_alpha;
+  m->device = device; m->D = D; m->H = H; m->depth = depth; m->p0 = transition_bias; m->alpha = crp_alpha;
   int rc = 0;
   auto body = [&]() -> int {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     m->num_sms = prop.multiProcessorCount;
     std::vector<float> v;
-    if (int r = fetch(v, w_ih, (size_t)3 * H * D)) return r;
-    { auto t = transpose(v, 3 * H, D); if (int r = upload(m->wih_t, t.data(), t.size() * 4)) return r; }
-    if (int r = fetch(v, w_hh, (size_t)3 * H * H)) return r;
-    { auto t = transpose(v, 3 * H, H); if (int r = upload(m->whh_t, t.data(), t.size() * 4)) return r; }
+    // w_ih = [layer 0: 3H x D | layers >= 1: 3H x H each]; w_hh = depth x [3H x H]; b_ih, b_hh = depth x [3H]
+    const size_t n_ih = (size_t)3 * H * D + (size_t)(depth - 1) * 3 * H * H;
+    if (int r = fetch(v, w_ih, n_ih)) return r;
+    {
+      std::vector<float> l0(v.begin(), v.begin() + (size_t)3 * H * D);
+      auto t = transpose(l0, 3 * H, D);
+      if (int r = upload(m->wih_t, t.data(), t.size() * 4)) return r;
+      std::vector<float> up;
+      for (int l = 1; l < depth; ++l) {
+        std::vector<float> w(v.begin() + (size_t)3 * H * D + (size_t)(l - 1) * 3 * H * H,
+                             v.begin() + (size_t)3 * H * D + (size_t)l * 3 * H * H);
+        auto tt = transpose(w, 3 * H, H);
+        up.insert(up.end(), tt.begin(), tt.end());
+      }
+      if (up.empty()) up.resize(4, 0.f);
+      if (int r = upload(m->wih_up_t, up.data(), up.size() * 4)) return r;
+    }
+    if (int r = fetch(v, w_hh, (size_t)depth * 3 * H * H)) return r;
+    {
+      std::vector<float> all;
+      for (int l = 0; l < depth; ++l) {
+        std::vector<float> w(v.begin() + (size_t)l * 3 * H * H, v.begin() + (size_t)(l + 1) * 3 * H * H);
+        auto tt = transpose(w, 3 * H, H);
+        all.insert(all.end(), tt.begin(), tt.end());
+      }
+      if (int r = upload(m->whh_t, all.data(), all.size() * 4)) return r;
+    }
     if (int r = fetch(v, w1, (size_t)H * H)) return r;
     { auto t = transpose(v, H, H); if (int r = upload(m->w1_t, t.data(), t.size() * 4)) return r; }
     if (int r = fetch(v, w2, (size_t)D * H)) return r;
     { auto t = transpose(v, D, H); if (int r = upload(m->w2_t, t.data(), t.size() * 4)) return r; }
-    if (int r = fetch(v, b_ih, 3 * H)) return r;
+    if (int r = fetch(v, b_ih, (size_t)depth * 3 * H)) return r;
     if (int r = upload(m->bih, v.data(), v.size() * 4)) return r;
-    if (int r = fetch(v, b_hh, 3 * H)) return r;
+    if (int r = fetch(v, b_hh, (size_t)depth * 3 * H)) return r;
     if (int r = upload(m->bhh, v.data(), v.size() * 4)) return r;
     if (int r = fetch(v, b1, H)) return r;
     if (int r = upload(m->b1, v.data(), v.size() * 4)) return r;
@@ -474,16 +506,16 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
     for (float& s : v) s = 1.0f / (2.0f * s);  // weight = 1 / (2 * sigma2), two fp32 ops (uisrnn.py:414)
     if (int r = upload(m->wvec, v.data(), v.size() * 4)) return r;
     std::vector<float> h0v;
-    if (int r = fetch(h0v, h0, H)) return r;
+    if (int r = fetch(h0v, h0, (size_t)depth * H)) return r;
     DevBuf h0d;
-    if (int r = upload(h0d, h0v.data(), H * 4)) return r;
+    if (int r = upload(h0d, h0v.data(), (size_t)depth * H * 4)) return r;
     if (int r = m->mean0.ensure(D * 4)) return r;
-    if (int r = m->hidden0.ensure(H * 4)) return r;
-    uis::init_state_kernel<<<1, H, 3 * H * sizeof(float)>>>(m->whh_t.as<float>(), m->w1_t.as<float>(),
-                                                           m->w2_t.as<float>(), m->bih.as<float>(),
-                                                           m->bhh.as<float>(), m->b1.as<float>(), m->b2.as<float>(),
-                                                           h0d.as<float>(), H, D, m->mean0.as<float>(),
-                                                           m->hidden0.as<float>());
+    if (int r = m->hidden0.ensure((size_t)depth * H * 4)) return r;
+    uis::init_state_kernel<<<1, H, 3 * H * sizeof(float)>>>(m->whh_t.as<float>(), m->wih_up_t.as<float>(),
+                                                           m->w1_t.as<float>(), m->w2_t.as<float>(),
+                                                           m->bih.as<float>(), m->bhh.as<float>(), m->b1.as<float>(),
+                                                           m->b2.as<float>(), h0d.as<float>(), H, D, depth,
+                                                           m->mean0.as<float>(), m->hidden0.as<float>());
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     h0d.release();
@@ -502,7 +534,7 @@ int uis_model_destroy(uis_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->device);
   DevBuf* bufs[] = {&m->wih_t, &m->whh_t, &m->w1_t, &m->w2_t, &m->bih, &m->bhh, &m->b1, &m->b2, &m->wvec, &m->mean0,
-                    &m->hidden0, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
+                    &m->hidden0, &m->wih_up_t, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
                     &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
                     &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
                     &m->dbg_best_hidden, &m->dbg_best_blocks};
@@ -517,7 +549,7 @@ int uis_model_constants(uis_model* m, float* mean0, float* hidden0) {
   if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
   CU(cudaSetDevice(m->device));
   if (mean0) CU(cudaMemcpy(mean0, m->mean0.p, m->D * 4, cudaMemcpyDeviceToHost));
-  if (hidden0) CU(cudaMemcpy(hidden0, m->hidden0.p, m->H * 4, cudaMemcpyDeviceToHost));
+  if (hidden0) CU(cudaMemcpy(hidden0, m->hidden0.p, (size_t)m->depth * m->H * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -38,6 +38,7 @@ constexpr int kStageBytes = 48 * 1024;  // bytes per ring stage
 constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
 constexpr int kCP = 16;                 // GRU columns per weight pass
 constexpr int kMaxLanes = 4;
+constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
 
 struct TabEntry {
   int slot;    // index into the lane's slot pool
@@ -49,6 +50,12 @@ struct TabEntry {
 struct BeamParams {
   // model (device pointers)
   const float* whh_t;    // [H][3H]   = gru.weight_hh_l0 transposed (k-major)
+  // stacked layers l = 1..depth-1 (nn.GRU feeds layer l with layer l-1's new hidden state):
+  const float* wih_up_t[kMaxDepth - 1];  // [H][3H] = gru.weight_ih_l{l} transposed
+  const float* whh_up_t[kMaxDepth - 1];  // [H][3H] = gru.weight_hh_l{l} transposed
+  const float* bih_up;   // [depth-1][3H]
+  const float* bhh_up;   // [depth-1][3H]
+  int depth;
   const float* w1_t;     // [H][H]    = linear_mean1.weight transposed
   const float* w2_t;     // [H][D]    = linear_mean2.weight transposed
   const float* bhh;      // [3H]
@@ -56,7 +63,7 @@ struct BeamParams {
   const float* b2;       // [D]
   const float* wvec;     // [D]  1 / (2 sigma2)
   const float* mean0;    // [D]
-  const float* hidden0;  // [H]
+  const float* hidden0;  // [depth][H]
   double log_p0, log_1mp0, log_alpha;
   const double* logn;    // [>= maxTN + 2]  log(i)
   const double* logtot;  // [>= maxTN + 2]  log(i + crp_alpha)
@@ -70,7 +77,7 @@ struct BeamParams {
   int dbg_mode;  // 0 normal; 1 = stream the weights but skip the math (timing experiment, results invalid)
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
-  float* pool_hidden;  // [ctas*G][P][H]
+  float* pool_hidden;  // [ctas*G][P][depth][H]
   unsigned* bp;        // [ctas*G][maxN][B]  (parent << 16) | cluster
   int* queue;          // [1] next position in `order`
   // outputs
@@ -86,7 +93,7 @@ struct BeamParams {
   float* dbg_final_scores; // [U][B]
   int* dbg_final_k;        // [U]
   float* dbg_best_mean;    // [Kcap][D]
-  float* dbg_best_hidden;  // [Kcap][H]
+  float* dbg_best_hidden;  // [Kcap][depth][H]
   int* dbg_best_blocks;    // [Kcap]
 };
 
@@ -185,10 +192,14 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
       __nanosleep(64);
     }
     __threadfence_block();
-    for (int seg = 0; seg < 3; ++seg) {
-      const float* src = seg == 0 ? p.whh_t : (seg == 1 ? p.w1_t : p.w2_t);
-      const int ntiles = seg == 0 ? C::N_HH : (seg == 1 ? C::N_1 : C::N_2);
-      const unsigned bytes = seg == 0 ? C::KT_HH * 3 * H * 4 : (seg == 1 ? C::KT_1 * H * 4 : C::KT_2 * D * 4);
+    const int ngru = 1 + 2 * (p.depth - 1);  // W_hh_0, then (W_ih_l, W_hh_l) for every upper layer
+    for (int seg = 0; seg < ngru + 2; ++seg) {
+      const float* src;
+      if (seg == 0) src = p.whh_t;
+      else if (seg < ngru) src = ((seg - 1) & 1) ? p.whh_up_t[(seg - 1) / 2] : p.wih_up_t[(seg - 1) / 2];
+      else src = (seg == ngru) ? p.w1_t : p.w2_t;
+      const int ntiles = seg < ngru ? C::N_HH : (seg == ngru ? C::N_1 : C::N_2);
+      const unsigned bytes = seg < ngru ? C::KT_HH * 3 * H * 4 : (seg == ngru ? C::KT_1 * H * 4 : C::KT_2 * D * 4);
       for (int t = 0; t < ntiles; ++t, ++it) {
         const unsigned s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
@@ -204,8 +215,9 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
 // Consume one full weight pass without computing (a step with no winner at all), so that the
 // producer, which was already told about the pass, never blocks on a full ring.
 template <class C>
-__device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsigned& it, int lane) {
-  for (int t = 0; t < C::TILES_PER_PASS; ++t, ++it) {
+__device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsigned& it, int lane, int depth = 1) {
+  const int tiles = C::TILES_PER_PASS + 2 * (depth - 1) * C::N_HH;
+  for (int t = 0; t < tiles; ++t, ++it) {
     const unsigned s = it % kStages, ph = (it / kStages) & 1;
     mbar_wait(&full[s], ph);
     __syncwarp();
@@ -225,7 +237,7 @@ struct Operands {
   float4 x[NC];
 };
 
-template <class C, int ROWS, int KT, int KG, int R, int NC>
+template <class C, int ROWS, int KT, int KG, int R, int NC, bool ZERO = true>
 __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
                                          unsigned& it, const float* __restrict__ X, float (&acc)[R][4 * NC],
                                          int tid, int lane) {
@@ -233,10 +245,12 @@ __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_
   constexpr int KPG = KT / KG;
   constexpr int NTILES = C::H / KT;
   const int kg = tid / TG, tl = tid % TG;
+  if constexpr (ZERO) {
 #pragma unroll
-  for (int i = 0; i < R; ++i)
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int m = 0; m < 4 * NC; ++m) acc[i][m] = 0.f;
+      for (int m = 0; m < 4 * NC; ++m) acc[i][m] = 0.f;
+  }
 
   auto tile_w = [&](unsigned itx) -> const float* {
     return ring + (size_t)(itx % kStages) * (kStageBytes / 4) + (size_t)(kg * KPG) * ROWS + tl;
@@ -365,7 +379,8 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
                                          float* pool_hidden_cta, const float (&bh)[C::RG], const float (&b1r)[C::UPT],
                                          float b2r, int tid, int lane, long long* ph, long long& tmark) {
   constexpr int H = C::H, D = C::D, NT = C::NT, UPT = C::UPT;
-  const size_t lane_pool_h = (size_t)p.P * H, lane_pool_m = (size_t)p.P * D;
+  const int DH = p.depth * H;
+  const size_t lane_pool_h = (size_t)p.P * DH, lane_pool_m = (size_t)p.P * D;
   // ---------------- GRU gates: acc[g*UPT + u][m] = (W_h{r,z,n} h_src)[unit tid + NT*u]
   {
     float acc[C::RG][4 * NC];
@@ -389,12 +404,75 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
             const float z = sigmoid_f32(__fadd_rn(gi[H + j], __fadd_rn(acc[1 * UPT + u][m], bh[1 * UPT + u])));
             const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(r, __fadd_rn(acc[2 * UPT + u][m], bh[2 * UPT + u]))));
             hn[q] = __fadd_rn(__fmul_rn(__fsub_rn(ho[q], n), z), n);
-            pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H + j] = hn[q];
+            pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * DH + j] = hn[q];
           }
         }
         reinterpret_cast<float4*>(XB + (size_t)j * kCP)[c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
       }
     }
+  }
+  // ---------------- stacked layers (nn.GRU depth >= 2, eval mode: no inter-layer dropout):
+  //   layer l sees x = h'_{l-1} (in XB) and its own previous state h_l (gathered into XA)
+  for (int l = 1; l < p.depth; ++l) {
+    named_bar_sync(1, NT);
+    float acc[C::RG][4 * NC];
+    lin_pass<C, 3 * H, C::KT_HH, 1, C::RG, NC>(ring, full, empty, it, XB, acc, tid, lane);  // W_ih_l h'_{l-1}
+    float ni[UPT][4 * NC];  // input part of the candidate gate stays separate: n = tanh(i_n + r * h_n)
+#pragma unroll
+    for (int u = 0; u < UPT; ++u)
+#pragma unroll
+      for (int m = 0; m < 4 * NC; ++m) { ni[u][m] = acc[2 * UPT + u][m]; acc[2 * UPT + u][m] = 0.f; }
+    named_bar_sync(1, NT);  // every thread is done with XA (layer l-1) ...
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) {  // ... which now receives h_l of the source slots
+      const int j = tid + NT * u;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = 4 * c + q;
+          hv[q] = (m < Mp) ? pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.src[m0 + m] * DH +
+                                             (size_t)l * H + j]
+                           : 0.f;
+        }
+        reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      }
+    }
+    named_bar_sync(1, NT);
+    lin_pass<C, 3 * H, C::KT_HH, 1, C::RG, NC, false>(ring, full, empty, it, XA, acc, tid, lane);  // += W_hh_l h_l
+    const float* bi = p.bih_up + (size_t)(l - 1) * 3 * H;
+    const float* bhl = p.bhh_up + (size_t)(l - 1) * 3 * H;
+    float hn_out[UPT][4 * NC];
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) {
+      const int j = tid + NT * u;
+      const float bir = bi[j], biz = bi[H + j], bin = bi[2 * H + j];
+      const float bhr = bhl[j], bhz = bhl[H + j], bhn = bhl[2 * H + j];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * kCP)[c];
+        const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = 4 * c + q;
+          const float r = sigmoid_f32(__fadd_rn(__fadd_rn(acc[0 * UPT + u][m], bir), bhr));
+          const float z = sigmoid_f32(__fadd_rn(__fadd_rn(acc[1 * UPT + u][m], biz), bhz));
+          const float n = tanhf(__fadd_rn(__fadd_rn(ni[u][m], bin), __fmul_rn(r, __fadd_rn(acc[2 * UPT + u][m], bhn))));
+          const float hnew = __fadd_rn(__fmul_rn(__fsub_rn(ho[q], n), z), n);
+          hn_out[u][m] = (m < Mp) ? hnew : 0.f;
+          if (m < Mp)
+            pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * DH + (size_t)l * H + j] = hnew;
+        }
+      }
+    }
+    named_bar_sync(1, NT);  // XB (this layer's input) is no longer read by anyone
+#pragma unroll
+    for (int u = 0; u < UPT; ++u)
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        reinterpret_cast<float4*>(XB + (size_t)(tid + NT * u) * kCP)[c] =
+            make_float4(hn_out[u][4 * c], hn_out[u][4 * c + 1], hn_out[u][4 * c + 2], hn_out[u][4 * c + 3]);
   }
   named_bar_sync(1, NT);
   if (tid == 0) { const long long now_ = clock64(); ph[2] += now_ - tmark; tmark = now_; }
@@ -485,7 +563,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   // ---------------- consumer threads (tid < NT); they synchronise on named barrier 1
   auto lane_base = [&](int g) -> unsigned char* { return smem + L.lanes + (size_t)g * L.lane_stride; };
   auto LSp = [&](int g) -> volatile int* { return reinterpret_cast<volatile int*>(lane_base(g) + L.l_ls); };
-  const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * H;
+  const int DH = p.depth * H;
+  const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * DH;
   float* pool_mean_cta = p.pool_mean + (size_t)blockIdx.x * G * pool_m_stride;
   float* pool_hidden_cta = p.pool_hidden + (size_t)blockIdx.x * G * pool_h_stride;
   unsigned* bp_cta = p.bp + (size_t)blockIdx.x * G * p.maxN * B;
@@ -501,8 +580,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   if (tid < D) wv[tid] = p.wvec[tid];
   for (int g = 0; g < G; ++g) {
     if (tid < D) pool_mean_cta[g * pool_m_stride + (size_t)kInitSlot * D + tid] = p.mean0[tid];
-    for (int u = 0; u < UPT; ++u)
-      pool_hidden_cta[g * pool_h_stride + (size_t)kInitSlot * H + tid + NT * u] = p.hidden0[tid + NT * u];
+    for (int q = tid; q < DH; q += NT) pool_hidden_cta[g * pool_h_stride + (size_t)kInitSlot * DH + q] = p.hidden0[q];
   }
 
   int* collane = colarr; int* colsrc = colarr + G * B; int* colnew = colarr + 2 * G * B;
@@ -907,7 +985,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
 
     UIS_PHASE(0);
     // ---- P5: GRU + MLP for the Mtot distinct source states, kCP columns per weight pass
-    if (Mtot == 0) drain_pass<C>(full, empty, it, lane);
+    if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth);
     for (int m0 = 0; m0 < Mtot; m0 += kCP) {
       const int Mp = min(kCP, Mtot - m0);
       // gather the source hidden states, transposed: XA[k][m]
@@ -921,7 +999,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
           for (int q = 0; q < 4; ++q) {
             const int m = 4 * c + q;
             hv[q] = (m < Mp) ? pool_hidden_cta[(size_t)collane[m0 + m] * pool_h_stride +
-                                               (size_t)colsrc[m0 + m] * H + j]
+                                               (size_t)colsrc[m0 + m] * DH + j]
                              : 0.f;
           }
           reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -930,7 +1008,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       named_bar_sync(1, NT);
       UIS_PHASE(1);
       const int nc = (Mp + 3) / 4;
-      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane);
+      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth);
       else if (nc == 1) run_pass<C, 1>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       else if (nc == 2) run_pass<C, 2>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       else if (nc == 3) run_pass<C, 3>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
@@ -967,9 +1045,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
         for (int c = 0; c < fK[0]; ++c) {  // best hypothesis = rank 0
           const TabEntry en = ftab[c];
           if (tid < D) p.dbg_best_mean[(size_t)c * D + tid] = pool_mean_cta[g * pool_m_stride + (size_t)en.slot * D + tid];
-          for (int uu = 0; uu < UPT; ++uu)
-            p.dbg_best_hidden[(size_t)c * H + tid + NT * uu] =
-                pool_hidden_cta[g * pool_h_stride + (size_t)en.slot * H + tid + NT * uu];
+          for (int q = tid; q < DH; q += NT)
+            p.dbg_best_hidden[(size_t)c * DH + q] = pool_hidden_cta[g * pool_h_stride + (size_t)en.slot * DH + q];
           if (tid == 0) p.dbg_best_blocks[c] = en.blocks;
         }
       }

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
   }
   if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
 
-  const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * H;
+  const int DH = p.depth * H;
+  const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * DH;
   float* pool_mean = p.pool_mean + (size_t)blockIdx.x * pool_m_stride;
   float* pool_hidden = p.pool_hidden + (size_t)blockIdx.x * pool_h_stride;
   unsigned* bp_lab = p.bp + (size_t)blockIdx.x * ((size_t)p.maxTN + p.maxSteps) * B;  // [frame][r] cluster
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
   for (int u = 0; u < UPT; ++u) b1r[u] = p.b1[tid + NT * u];
   const float b2r = (tid < D) ? p.b2[tid] : 0.f;
   if (tid < D) { wv[tid] = p.wvec[tid]; pool_mean[(size_t)kInitSlot * D + tid] = p.mean0[tid]; }
-  for (int u = 0; u < UPT; ++u) pool_hidden[(size_t)kInitSlot * H + tid + NT * u] = p.hidden0[tid + NT * u];
+  for (int q = tid; q < DH; q += NT) pool_hidden[(size_t)kInitSlot * DH + q] = p.hidden0[q];
   for (int i = tid; i < NI; i += NT) collane[i] = 0;
   const ColCtx cc{collane, colsrc, colnew, colvis, nullptr, colrow};
 
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
     }
     named_bar_sync(1, NT);
     if (misc[TM_ERR]) {  // keep the producer protocol consistent, skip the math
-      for (int q = 0; q < npass; ++q) drain_pass<C>(full, empty, it, lane);
+      for (int q = 0; q < npass; ++q) drain_pass<C>(full, empty, it, lane, p.depth);
       return;
     }
     for (int m0 = 0; m0 < M; m0 += kCP) {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int m = 4 * c4 + q;
-            hv[q] = (m < Mp) ? pool_hidden[(size_t)colsrc[m0 + m] * H + j] : 0.f;
+            hv[q] = (m < Mp) ? pool_hidden[(size_t)colsrc[m0 + m] * DH + j] : 0.f;
           }
           reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
@@ -484,8 +485,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
       for (int c = 0; c < K0; ++c) {
         const TabEntry en = ftab[c];
         if (tid < D) p.dbg_best_mean[(size_t)c * D + tid] = pool_mean[(size_t)en.slot * D + tid];
-        for (int uu = 0; uu < UPT; ++uu)
-          p.dbg_best_hidden[(size_t)c * H + tid + NT * uu] = pool_hidden[(size_t)en.slot * H + tid + NT * uu];
+        for (int q = tid; q < DH; q += NT) p.dbg_best_hidden[(size_t)c * DH + q] = pool_hidden[(size_t)en.slot * DH + q];
         if (tid == 0) p.dbg_best_blocks[c] = en.blocks;
       }
     }

@@ -88,36 +88,55 @@ __global__ void __launch_bounds__(256) input_proj_kernel(const float* __restrict
 }
 
 // One CTA of H threads.  Weights in the k-major layouts used by the beam kernel.
-__global__ void init_state_kernel(const float* __restrict__ whh_t, const float* __restrict__ w1_t,
-                                  const float* __restrict__ w2_t, const float* __restrict__ bih,
-                                  const float* __restrict__ bhh, const float* __restrict__ b1,
-                                  const float* __restrict__ b2, const float* __restrict__ h0, int H, int D,
-                                  float* __restrict__ mean0, float* __restrict__ hidden0) {
-  extern __shared__ float sm[];  // [H] h0, [H] h', [H] act
-  float* sh0 = sm; float* sh1 = sm + H; float* sa = sm + 2 * H;
+// whh_t: [depth][H][3H]; wih_up_t: [depth-1][H][3H] (layers >= 1); bih: [depth][3H]; bhh: [depth][3H]; h0: [depth][H].
+__global__ void init_state_kernel(const float* __restrict__ whh_t, const float* __restrict__ wih_up_t,
+                                  const float* __restrict__ w1_t, const float* __restrict__ w2_t,
+                                  const float* __restrict__ bih, const float* __restrict__ bhh,
+                                  const float* __restrict__ b1, const float* __restrict__ b2,
+                                  const float* __restrict__ h0, int H, int D, int depth, float* __restrict__ mean0,
+                                  float* __restrict__ hidden0) {
+  extern __shared__ float sm[];  // [H] layer state, [H] layer input / output, [H] act
+  float* shp = sm; float* shx = sm + H; float* sa = sm + 2 * H;
   const int j = threadIdx.x;
-  if (j < H) sh0[j] = h0[j];
-  __syncthreads();
-  if (j < H) {
-    float ar = 0.f, az = 0.f, an = 0.f;
-    for (int k = 0; k < H; ++k) {
-      const float x = sh0[k];
-      ar = fmaf(whh_t[(size_t)k * 3 * H + j], x, ar);
-      az = fmaf(whh_t[(size_t)k * 3 * H + H + j], x, az);
-      an = fmaf(whh_t[(size_t)k * 3 * H + 2 * H + j], x, an);
+  for (int l = 0; l < depth; ++l) {
+    if (j < H) shp[j] = h0[(size_t)l * H + j];
+    __syncthreads();
+    float hn = 0.f;
+    if (j < H) {
+      const float* wh = whh_t + (size_t)l * H * 3 * H;
+      float ar = 0.f, az = 0.f, an = 0.f;
+      for (int k = 0; k < H; ++k) {
+        const float x = shp[k];
+        ar = fmaf(wh[(size_t)k * 3 * H + j], x, ar);
+        az = fmaf(wh[(size_t)k * 3 * H + H + j], x, az);
+        an = fmaf(wh[(size_t)k * 3 * H + 2 * H + j], x, an);
+      }
+      // layer 0: x = 0  =>  W_ih x + b_ih = b_ih exactly; layer l >= 1: x = h'_{l-1}
+      float ir = 0.f, iz = 0.f, in = 0.f;
+      if (l > 0) {
+        const float* wi = wih_up_t + (size_t)(l - 1) * H * 3 * H;
+        for (int k = 0; k < H; ++k) {
+          const float x = shx[k];
+          ir = fmaf(wi[(size_t)k * 3 * H + j], x, ir);
+          iz = fmaf(wi[(size_t)k * 3 * H + H + j], x, iz);
+          in = fmaf(wi[(size_t)k * 3 * H + 2 * H + j], x, in);
+        }
+      }
+      const float* bi = bih + (size_t)l * 3 * H;
+      const float* bh = bhh + (size_t)l * 3 * H;
+      const float r = sigmoid_f32(__fadd_rn(__fadd_rn(ir, bi[j]), __fadd_rn(ar, bh[j])));
+      const float z = sigmoid_f32(__fadd_rn(__fadd_rn(iz, bi[H + j]), __fadd_rn(az, bh[H + j])));
+      const float n = tanhf(__fadd_rn(__fadd_rn(in, bi[2 * H + j]), __fmul_rn(r, __fadd_rn(an, bh[2 * H + j]))));
+      hn = __fadd_rn(__fmul_rn(__fsub_rn(shp[j], n), z), n);
+      hidden0[(size_t)l * H + j] = hn;
     }
-    // x = 0  =>  W_ih x + b_ih = b_ih exactly
-    const float r = sigmoid_f32(__fadd_rn(bih[j], __fadd_rn(ar, bhh[j])));
-    const float z = sigmoid_f32(__fadd_rn(bih[H + j], __fadd_rn(az, bhh[H + j])));
-    const float n = tanhf(__fadd_rn(bih[2 * H + j], __fmul_rn(r, __fadd_rn(an, bhh[2 * H + j]))));
-    const float hn = __fadd_rn(__fmul_rn(__fsub_rn(sh0[j], n), z), n);
-    sh1[j] = hn;
-    hidden0[j] = hn;
+    __syncthreads();
+    if (j < H) shx[j] = hn;
+    __syncthreads();
   }
-  __syncthreads();
   if (j < H) {
     float a = 0.f;
-    for (int k = 0; k < H; ++k) a = fmaf(w1_t[(size_t)k * H + j], sh1[k], a);
+    for (int k = 0; k < H; ++k) a = fmaf(w1_t[(size_t)k * H + j], shx[k], a);
     sa[j] = fmaxf(__fadd_rn(a, b1[j]), 0.f);
   }
   __syncthreads();

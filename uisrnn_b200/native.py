@@ -144,12 +144,18 @@ class NativeModel:
     self.H = int(np.asarray(w['w1']).shape[0])
     self.D = int(np.asarray(w['w2']).shape[0])
     self.device = device
-    arrs = [_f32(w['weight_ih_l0']), _f32(w['weight_hh_l0']), _f32(w['bias_ih_l0']),
-            _f32(w['bias_hh_l0']), _f32(w['w1']), _f32(w['b1']), _f32(w['w2']), _f32(w['b2']),
-            _f32(np.asarray(w['h0']).reshape(-1)[:self.H] if depth == 1 else w['h0']),
-            _f32(w['sigma2'])]
-    expect = [(3 * self.H, self.D), (3 * self.H, self.H), (3 * self.H,), (3 * self.H,),
-              (self.H, self.H), (self.H,), (self.D, self.H), (self.D,), None, (self.D,)]
+    self.depth = depth
+    H, D = self.H, self.D
+    layers = range(depth)
+    for l in layers:  # PyTorch nn.GRU layouts: layer 0 sees the observation, layer l >= 1 sees layer l-1
+      if tuple(np.asarray(w['weight_ih_l%d' % l]).shape) != (3 * H, D if l == 0 else H) or \
+         tuple(np.asarray(w['weight_hh_l%d' % l]).shape) != (3 * H, H):
+        raise ValueError('GRU weight shapes of layer %d do not match hidden=%d dim=%d' % (l, H, D))
+    cat = lambda key: _f32(np.concatenate([np.asarray(w['%s_l%d' % (key, l)], np.float32).reshape(-1) for l in layers]))
+    arrs = [cat('weight_ih'), cat('weight_hh'), cat('bias_ih'), cat('bias_hh'),
+            _f32(w['w1']), _f32(w['b1']), _f32(w['w2']), _f32(w['b2']),
+            _f32(np.asarray(w['h0']).reshape(-1)), _f32(w['sigma2'])]
+    expect = [None, None, (depth * 3 * H,), (depth * 3 * H,), (H, H), (H,), (D, H), (D,), (depth * H,), (D,)]
     for a, e in zip(arrs, expect):
       if e is not None and tuple(a.shape) != e:
         raise ValueError('weight shape {} != expected {}'.format(a.shape, e))
@@ -170,7 +176,7 @@ class NativeModel:
 
   def constants(self):
     mean0 = np.empty(self.D, np.float32)
-    hidden0 = np.empty(self.H, np.float32)
+    hidden0 = np.empty((self.depth, self.H), np.float32)
     fp = C.POINTER(C.c_float)
     _check(self._lib, self._lib.uis_model_constants(self._h, mean0.ctypes.data_as(fp),
                                                     hidden0.ctypes.data_as(fp)))
@@ -193,7 +199,7 @@ class NativeModel:
         'final_scores': np.zeros((n_utt, beam_size), np.float32),
         'final_k': np.zeros(n_utt, np.int32),
         'best_mean': np.zeros((kcap, self.D), np.float32),
-        'best_hidden': np.zeros((kcap, self.H), np.float32),
+        'best_hidden': np.zeros((kcap, self.depth, self.H), np.float32),
         'best_blocks': np.zeros(kcap, np.int32),
     }
     fp, ip, lp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
