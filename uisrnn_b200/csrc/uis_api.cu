@@ -17,6 +17,7 @@
 #include "../../include/uisrnn_b200.h"
 #include "uis_beam.cuh"
 #include "uis_beam_tree.cuh"
+#include "uis_launch.cuh"
 #include "uis_prepass.cuh"
 
 namespace {
@@ -103,37 +104,11 @@ struct uis_model {
 
 namespace {
 
-template <int H, int D>
-int launch_beam(const uis::BeamParams& p, int ctas, cudaStream_t st) {
-  const uis::SmemLayout L = uis::make_layout<H, D>(p.B, p.Kcap, p.G);
-  if (L.total > 227 * 1024)
-    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d lanes=%d needs %u B of shared memory (> 227 KB); lower kcap",
-                p.B, p.Kcap, p.G, L.total);
-  auto kern = uis::uis_beam_kernel<H, D>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  kern<<<ctas, uis::Cfg<H, D>::BLOCK, L.total, st>>>(p);
-  CU(cudaGetLastError());
-  return 0;
-}
-
 unsigned smem_bytes(int H, int D, int B, int Kcap, int G) {
   if (H == 512 && D == 256) return uis::make_layout<512, 256>(B, Kcap, G).total;
   if (H == 256 && D == 128) return uis::make_layout<256, 128>(B, Kcap, G).total;
   if (H == 128 && D == 64) return uis::make_layout<128, 64>(B, Kcap, G).total;
   return 0xffffffffu;
-}
-
-template <int H, int D>
-int launch_tree(const uis::BeamParams& p, int ctas, cudaStream_t st) {
-  const uis::TreeLayout T = uis::make_tree_layout<H, D>(p.B, p.Kcap, p.L, p.node_cap, p.leaf_cap, p.P);
-  if (T.total > 227 * 1024)
-    return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d beam_size=%d kcap=%d needs %u B of shared memory (> 227 KB)", p.L,
-                p.B, p.Kcap, T.total);
-  auto kern = uis::uis_beam_tree_kernel<H, D>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total));
-  kern<<<ctas, uis::Cfg<H, D>::BLOCK, T.total, st>>>(p);
-  CU(cudaGetLastError());
-  return 0;
 }
 
 unsigned tree_smem_bytes(int H, int D, int B, int Kcap, int L, int NI, int NLF, int P) {
@@ -144,10 +119,15 @@ unsigned tree_smem_bytes(int H, int D, int B, int Kcap, int L, int NI, int NLF, 
 }
 
 int dispatch_tree(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t st) {
-  if (H == 512 && D == 256) return launch_tree<512, 256>(p, ctas, st);
-  if (H == 256 && D == 128) return launch_tree<256, 128>(p, ctas, st);
-  if (H == 128 && D == 64) return launch_tree<128, 64>(p, ctas, st);
-  return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  const unsigned smem = tree_smem_bytes(H, D, p.B, p.Kcap, p.L, p.node_cap, p.leaf_cap, p.P);
+  if (smem > 227u * 1024u)
+    return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d beam_size=%d kcap=%d needs %u B of shared memory (> 227 KB)", p.L,
+                p.B, p.Kcap, smem);
+  cudaError_t e = cudaSuccess;
+  if (!uis::launch_tree_large(H, D, p, ctas, smem, st, &e) && !uis::launch_tree_small(H, D, p, ctas, smem, st, &e))
+    return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "look-ahead kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 bool shape_supported(int H, int D) {
@@ -155,10 +135,15 @@ bool shape_supported(int H, int D) {
 }
 
 int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t st) {
-  if (H == 512 && D == 256) return launch_beam<512, 256>(p, ctas, st);
-  if (H == 256 && D == 128) return launch_beam<256, 128>(p, ctas, st);
-  if (H == 128 && D == 64) return launch_beam<128, 64>(p, ctas, st);
-  return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  const unsigned smem = smem_bytes(H, D, p.B, p.Kcap, p.G);
+  if (smem > 227u * 1024u)
+    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d lanes=%d needs %u B of shared memory (> 227 KB); lower kcap",
+                p.B, p.Kcap, p.G, smem);
+  cudaError_t e = cudaSuccess;
+  if (!uis::launch_beam_large(H, D, p, ctas, smem, st, &e) && !uis::launch_beam_small(H, D, p, ctas, smem, st, &e))
+    return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "beam kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int fetch(std::vector<float>& dst, const float* src, size_t n) {

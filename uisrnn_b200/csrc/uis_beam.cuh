@@ -36,7 +36,8 @@ namespace uis {
 constexpr int kStages = 2;              // weight ring depth
 constexpr int kStageBytes = 48 * 1024;  // bytes per ring stage
 constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
-constexpr int kCP = 16;                 // GRU columns per weight pass
+constexpr int kCPBeam = 20;             // GRU columns per weight pass, look_ahead-1 kernel (two lanes need <= 20 in ~99 % of the steps)
+constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
 constexpr int kMaxLanes = 4;
 constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
 
@@ -102,9 +103,10 @@ template <> struct Pow2Floor<1> { static constexpr int value = 1; };
 template <> struct Pow2Floor<0> { static constexpr int value = 1; };
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int H_, int D_>
+template <int H_, int D_, int CP_ = kCPBeam>
 struct Cfg {
   static constexpr int H = H_, D = D_;
+  static constexpr int CP = CP_;                  // columns per weight pass = row stride of XA / XB
   static constexpr int UPT = (H >= 512) ? 2 : 1;  // hidden units per consumer thread
   static constexpr int NT = H / UPT;              // consumer threads
   static constexpr int NW = NT / 32;
@@ -128,13 +130,12 @@ struct Cfg {
   static_assert(TG2 * R2 == D && TG1 * R1 == H, "row split");
   static_assert(KG1 * H <= 2 * H && KG2 * D <= 2 * H, "K-split scratch must fit in XA+XB");
   static_assert(D % 4 == 0 && NT % 32 == 0 && D <= NT, "shape");
-  static_assert((3 * H / 4) + (D / 4) <= NT * 2, "prefetch mapping");
 };
 
 struct SmemLayout {
   unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, total;
   // offsets inside one lane block
-  unsigned l_xt, l_gi, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
+  unsigned l_xt, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -148,6 +149,7 @@ enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT };
 
 template <int H, int D>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
+  constexpr int kCP = kCPBeam;
   SmemLayout L;
   unsigned o = 0;
   L.ring = o;  o += kStages * kStageBytes;
@@ -157,7 +159,6 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   // ---- one lane block
   unsigned q = 0;
   L.l_xt = q;      q += 2 * D * 4;
-  L.l_gi = q;      q += 2 * 3 * H * 4;
   L.l_tabs = q;    q += 2u * B * Kcap * 16;
   L.l_meta = q;    q += 2u * 4 * B * 4;  // K,last,tot,nl  x2 generations
   L.l_candoff = q; q += align_up((B + 1) * 4, 16);
@@ -172,7 +173,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   L.l_ls = q;      q += LS_COUNT * 4;
   L.lane_stride = align_up(q, 16);
   L.lanes = o;     o += L.lane_stride * G;
-  L.cols = o;      o += align_up(5u * G * B * 4, 16);  // collane, colsrc, colnew, colvis, colgi
+  L.cols = o;      o += align_up(6u * G * B * 4, 16);  // collane, colsrc, colnew, colvis, colrow (8 B each)
   L.bars = o;      o += 2 * kStages * 8;
   L.misc = o;      o += 64;
   L.total = o;
@@ -227,7 +228,7 @@ __device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsi
 
 // ------------------------------------------------------------------ consumer: one weight matrix
 // acc[i][m] += sum_k Wt[k][tl + TG*i] * X[k][m]   for this thread's R rows and its K-group's
-// share (KT/KG k-rows) of every ring tile.  Wt tiles are [KT][ROWS] floats; X is [H][kCP].
+// share (KT/KG k-rows) of every ring tile.  Wt tiles are [KT][ROWS] floats; X is [H][C::CP].
 // The operand loads are software-pipelined ACROSS ring tiles: the first k-step of tile t+1 is
 // fetched (after its full-barrier test) before the last k-step of tile t is multiplied, so the
 // mbarrier round trip and the shared-memory latency are not exposed at every tile boundary.
@@ -256,14 +257,14 @@ __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_
     return ring + (size_t)(itx % kStages) * (kStageBytes / 4) + (size_t)(kg * KPG) * ROWS + tl;
   };
   auto tile_x = [&](int tile) -> const float4* {
-    return reinterpret_cast<const float4*>(X + (size_t)(tile * KT + kg * KPG) * kCP);
+    return reinterpret_cast<const float4*>(X + (size_t)(tile * KT + kg * KPG) * C::CP);
   };
   // volatile ld.shared: keeps the loads of k-step s+1 AHEAD of the FFMA2s of k-step s in the
   // instruction stream (the compiler otherwise sinks them next to their first use, which
   // exposes the ~30-cycle shared-memory latency with only 2 warps per scheduler)
   auto load = [&](Operands<R, NC>& o, const float* wt, const float4* xp, int kq) {
     const uint32_t wa = smem_u32(wt) + (uint32_t)(kq * ROWS) * 4u;
-    const uint32_t xa = smem_u32(xp) + (uint32_t)(kq * (kCP / 4)) * 16u;
+    const uint32_t xa = smem_u32(xp) + (uint32_t)(kq * (C::CP / 4)) * 16u;
 #pragma unroll
     for (int i = 0; i < R; ++i)
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.w[i]) : "r"(wa + (uint32_t)(TG * i) * 4u));
@@ -319,7 +320,7 @@ __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_
 }
 
 // Sum the K-groups' partial results through shared memory.  On return out[q][m] holds the full
-// sum for row tid + NT*q (q < RF).  `scratch` = XA..XB (2*H*kCP floats), dead at this point.
+// sum for row tid + NT*q (q < RF).  `scratch` = XA..XB (2*H*C::CP floats), dead at this point.
 template <class C, int ROWS, int KG, int R, int RF, int NC>
 __device__ __forceinline__ void ksplit_reduce(float (&acc)[R][4 * NC], float* __restrict__ scratch,
                                               float (&out)[RF][4 * NC], int tid) {
@@ -337,7 +338,7 @@ __device__ __forceinline__ void ksplit_reduce(float (&acc)[R][4 * NC], float* __
     for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int c = 0; c < NC; ++c)
-        reinterpret_cast<float4*>(scratch + ((size_t)kg * ROWS + tl + TG * i) * kCP)[c] =
+        reinterpret_cast<float4*>(scratch + ((size_t)kg * ROWS + tl + TG * i) * C::CP)[c] =
             make_float4(acc[i][4 * c + 0], acc[i][4 * c + 1], acc[i][4 * c + 2], acc[i][4 * c + 3]);
     named_bar_sync(1, C::NT);
 #pragma unroll
@@ -347,10 +348,10 @@ __device__ __forceinline__ void ksplit_reduce(float (&acc)[R][4 * NC], float* __
       for (int c = 0; c < NC; ++c) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < ROWS) {
-          v = reinterpret_cast<const float4*>(scratch + (size_t)row * kCP)[c];
+          v = reinterpret_cast<const float4*>(scratch + (size_t)row * C::CP)[c];
 #pragma unroll
           for (int g = 1; g < KG; ++g) {
-            const float4 o = reinterpret_cast<const float4*>(scratch + ((size_t)g * ROWS + row) * kCP)[c];
+            const float4 o = reinterpret_cast<const float4*>(scratch + ((size_t)g * ROWS + row) * C::CP)[c];
             v.x = __fadd_rn(v.x, o.x); v.y = __fadd_rn(v.y, o.y); v.z = __fadd_rn(v.z, o.z); v.w = __fadd_rn(v.w, o.w);
           }
         }
@@ -367,14 +368,13 @@ struct ColCtx {
   const int* src;   // source slot
   const int* dst;   // new slot
   const int* vis;   // visits of the source entry BEFORE this update
-  const int* gi;    // float offset (from smem base) of the lane's current gi row   (GIG == false)
-  const long long* girow;  // row of p.gi holding W_ih x + b_ih for the column's frame (GIG == true)
+  const long long* girow;  // row of p.gi (= W_ih x + b_ih, written by input_proj_kernel) of the column's frame
 };
 
 // ---- one full weight pass (GRU -> W1 -> W2) for columns [m0, m0 + Mp) -----------------------
-template <class C, int NC, bool GIG = false>
+template <class C, int NC, bool DEEP>
 __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
-                                         unsigned& it, float* XA, float* XB, const float* smem_f,
+                                         unsigned& it, float* XA, float* XB,
                                          const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
                                          float* pool_hidden_cta, const float (&bh)[C::RG], const float (&b1r)[C::UPT],
                                          float b2r, int tid, int lane, long long* ph, long long& tmark) {
@@ -391,7 +391,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
       const int j = tid + NT * u;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * kCP)[c];
+        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * C::CP)[c];
         const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
         float hn[4];
 #pragma unroll
@@ -399,7 +399,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
           const int m = 4 * c + q;
           hn[q] = 0.f;
           if (m < Mp) {
-            const float* gi = GIG ? p.gi + (size_t)cc.girow[m0 + m] * 3 * H : smem_f + cc.gi[m0 + m];
+            const float* gi = p.gi + (size_t)cc.girow[m0 + m] * 3 * H;  // L2-resident, re-read per column (L1 hit)
             const float r = sigmoid_f32(__fadd_rn(gi[j], __fadd_rn(acc[0 * UPT + u][m], bh[0 * UPT + u])));
             const float z = sigmoid_f32(__fadd_rn(gi[H + j], __fadd_rn(acc[1 * UPT + u][m], bh[1 * UPT + u])));
             const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(r, __fadd_rn(acc[2 * UPT + u][m], bh[2 * UPT + u]))));
@@ -407,12 +407,13 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
             pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * DH + j] = hn[q];
           }
         }
-        reinterpret_cast<float4*>(XB + (size_t)j * kCP)[c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        reinterpret_cast<float4*>(XB + (size_t)j * C::CP)[c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
       }
     }
   }
   // ---------------- stacked layers (nn.GRU depth >= 2, eval mode: no inter-layer dropout):
   //   layer l sees x = h'_{l-1} (in XB) and its own previous state h_l (gathered into XA)
+  if constexpr (DEEP)
   for (int l = 1; l < p.depth; ++l) {
     named_bar_sync(1, NT);
     float acc[C::RG][4 * NC];
@@ -436,7 +437,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
                                              (size_t)l * H + j]
                            : 0.f;
         }
-        reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        reinterpret_cast<float4*>(XA + (size_t)j * C::CP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
       }
     }
     named_bar_sync(1, NT);
@@ -451,7 +452,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
       const float bhr = bhl[j], bhz = bhl[H + j], bhn = bhl[2 * H + j];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * kCP)[c];
+        const float4 hold = reinterpret_cast<const float4*>(XA + (size_t)j * C::CP)[c];
         const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -471,7 +472,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
     for (int u = 0; u < UPT; ++u)
 #pragma unroll
       for (int c = 0; c < NC; ++c)
-        reinterpret_cast<float4*>(XB + (size_t)(tid + NT * u) * kCP)[c] =
+        reinterpret_cast<float4*>(XB + (size_t)(tid + NT * u) * C::CP)[c] =
             make_float4(hn_out[u][4 * c], hn_out[u][4 * c + 1], hn_out[u][4 * c + 2], hn_out[u][4 * c + 3]);
   }
   named_bar_sync(1, NT);
@@ -489,7 +490,7 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
         float4 v;
         v.x = fmaxf(__fadd_rn(out[u][4 * c + 0], b1r[u]), 0.f); v.y = fmaxf(__fadd_rn(out[u][4 * c + 1], b1r[u]), 0.f);
         v.z = fmaxf(__fadd_rn(out[u][4 * c + 2], b1r[u]), 0.f); v.w = fmaxf(__fadd_rn(out[u][4 * c + 3], b1r[u]), 0.f);
-        reinterpret_cast<float4*>(XA + (size_t)(tid + NT * u) * kCP)[c] = v;
+        reinterpret_cast<float4*>(XA + (size_t)(tid + NT * u) * C::CP)[c] = v;
       }
   }
   named_bar_sync(1, NT);
@@ -523,8 +524,25 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
   }
 }
 
+// Picks the instantiation by NC = number of 4-column chunks in this pass.  DEEP (stacked GRU layers) is a
+// template parameter of the kernels so that the depth-1 kernels carry none of that code or its registers.
+template <class C, bool DEEP>
+__device__ __forceinline__ void run_pass_any(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
+                                             unsigned& it, float* XA, float* XB, const ColCtx cc, int m0, int Mp,
+                                             float* pool_mean_cta, float* pool_hidden_cta, const float (&bh)[C::RG],
+                                             const float (&b1r)[C::UPT], float b2r, int tid, int lane, long long* ph,
+                                             long long& tmark) {
+  const int nc = (Mp + 3) / 4;
+#define UIS_RP(NCV, DEEPV) \
+  run_pass<C, NCV, DEEPV>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark)
+  if (nc == 1) UIS_RP(1, DEEP); else if (nc == 2) UIS_RP(2, DEEP); else if (nc == 3) UIS_RP(3, DEEP);
+  else if (nc == 4 || C::CP < 20) UIS_RP(4, DEEP);
+  else { if constexpr (C::CP >= 20) UIS_RP(5, DEEP); }
+#undef UIS_RP
+}
+
 // ------------------------------------------------------------------ the kernel
-template <int H, int D>
+template <int H, int D, bool DEEP>
 __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const BeamParams p) {
   using C = Cfg<H, D>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
@@ -584,8 +602,9 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   }
 
   int* collane = colarr; int* colsrc = colarr + G * B; int* colnew = colarr + 2 * G * B;
-  int* colvis = colarr + 3 * G * B; int* colgi = colarr + 4 * G * B;
-  const ColCtx cc{collane, colsrc, colnew, colvis, colgi, nullptr};
+  int* colvis = colarr + 3 * G * B;
+  long long* colrow = reinterpret_cast<long long*>(colarr + 4 * G * B);
+  const ColCtx cc{collane, colsrc, colnew, colvis, colrow};
 
   unsigned it = 0;  // weight-ring tile counter (identical in every consumer thread)
   unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;
@@ -634,12 +653,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
     volatile int* ls = LSp(g);
     const long long row0 = ((long long)ls[LS_ROW0_HI] << 32) | (unsigned)ls[LS_ROW0_LO];
     const long long r = row0 + (t % ls[LS_N]);
-    float* gis = reinterpret_cast<float*>(lane_base(g) + L.l_gi) + (t & 1) * 3 * H;
     float* xts = reinterpret_cast<float*>(lane_base(g) + L.l_xt) + (t & 1) * D;
-    for (int q = tid; q < 3 * H / 4 + D / 4; q += NT) {
-      if (q < 3 * H / 4) cp_async16(gis + q * 4, p.gi + (size_t)r * 3 * H + q * 4);
-      else cp_async16(xts + (q - 3 * H / 4) * 4, p.x + (size_t)r * D + (q - 3 * H / 4) * 4);
-    }
+    for (int q = tid; q < D / 4; q += NT) cp_async16(xts + q * 4, p.x + (size_t)r * D + q * 4);
   };
 
   if (tid < G) lane_fetch(tid);
@@ -969,9 +984,13 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       collane[f] = g;
       colsrc[f] = lcolsrc[lc];
       colnew[f] = lcolsrc[B + lc];
-      colgi[f] = (int)((L.lanes + (size_t)g * L.lane_stride + L.l_gi) / 4) + (LSp(g)[LS_T] & 1) * 3 * H;
+      {
+        volatile int* lsg = LSp(g);
+        const long long row0g = ((long long)lsg[LS_ROW0_HI] << 32) | (unsigned)lsg[LS_ROW0_LO];
+        colrow[f] = row0g + (lsg[LS_T] % lsg[LS_N]);
+      }
     }
-    const int npass = max(1, (Mtot + kCP - 1) / kCP);
+    const int npass = max(1, (Mtot + C::CP - 1) / C::CP);
     if (tid == 0) {
       for (int g = 0; g < G; ++g) {
         volatile int* ls = LSp(g);
@@ -984,16 +1003,16 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
     named_bar_sync(1, NT);
 
     UIS_PHASE(0);
-    // ---- P5: GRU + MLP for the Mtot distinct source states, kCP columns per weight pass
+    // ---- P5: GRU + MLP for the Mtot distinct source states, C::CP columns per weight pass
     if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth);
-    for (int m0 = 0; m0 < Mtot; m0 += kCP) {
-      const int Mp = min(kCP, Mtot - m0);
+    for (int m0 = 0; m0 < Mtot; m0 += C::CP) {
+      const int Mp = min(C::CP, Mtot - m0);
       // gather the source hidden states, transposed: XA[k][m]
 #pragma unroll
       for (int u = 0; u < UPT; ++u) {
         const int j = tid + NT * u;
 #pragma unroll
-        for (int c = 0; c < kCP / 4; ++c) {
+        for (int c = 0; c < C::CP / 4; ++c) {
           float hv[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1002,17 +1021,13 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
                                                (size_t)colsrc[m0 + m] * DH + j]
                              : 0.f;
           }
-          reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          reinterpret_cast<float4*>(XA + (size_t)j * C::CP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
       }
       named_bar_sync(1, NT);
       UIS_PHASE(1);
-      const int nc = (Mp + 3) / 4;
       if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth);
-      else if (nc == 1) run_pass<C, 1>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
-      else if (nc == 2) run_pass<C, 2>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
-      else if (nc == 3) run_pass<C, 3>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
-      else run_pass<C, 4>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      else run_pass_any<C, DEEP>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
       named_bar_sync(1, NT);
       UIS_PHASE(4);
     }

@@ -23,6 +23,7 @@ struct TreeLayout {
 
 template <int H, int D>
 __host__ __device__ inline TreeLayout make_tree_layout(int B, int Kcap, int L, int NI, int NLF, int P) {
+  constexpr int kCP = kCPTree;
   TreeLayout T;
   unsigned o = 0;
   T.ring = o;     o += kStages * kStageBytes;
@@ -57,9 +58,9 @@ __host__ __device__ inline TreeLayout make_tree_layout(int B, int Kcap, int L, i
 
 enum { TM_PUBLISHED = 0, TM_DONE, TM_UIDX, TM_ERR, TM_NFINITE, TM_M, TM_COUNT, TM_NWIN };
 
-template <int H, int D>
-__global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(const BeamParams p) {
-  using C = Cfg<H, D>;
+template <int H, int D, bool DEEP>
+__global__ void __launch_bounds__(Cfg<H, D, kCPTree>::BLOCK, 1) uis_beam_tree_kernel(const BeamParams p) {
+  using C = Cfg<H, D, kCPTree>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int B = p.B, Kcap = p.Kcap, L = p.L, NI = p.node_cap, NLF = p.leaf_cap;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
   if (tid < D) { wv[tid] = p.wvec[tid]; pool_mean[(size_t)kInitSlot * D + tid] = p.mean0[tid]; }
   for (int q = tid; q < DH; q += NT) pool_hidden[(size_t)kInitSlot * DH + q] = p.hidden0[q];
   for (int i = tid; i < NI; i += NT) collane[i] = 0;
-  const ColCtx cc{collane, colsrc, colnew, colvis, nullptr, colrow};
+  const ColCtx cc{collane, colsrc, colnew, colvis, colrow};
 
   unsigned it = 0;
   unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
       colvis[col] = n_ov[n].visits;  // same source slot => same visit count
     }
     for (int m = tid; m < M; m += NT) colrow[m] = girow;
-    const int npass = (M + kCP - 1) / kCP;
+    const int npass = (M + C::CP - 1) / C::CP;
     if (tid == 0 && npass > 0) {
       st_cols += M; st_pass += npass;
       __threadfence_block();
@@ -206,28 +207,24 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_tree_kernel(cons
       for (int q = 0; q < npass; ++q) drain_pass<C>(full, empty, it, lane, p.depth);
       return;
     }
-    for (int m0 = 0; m0 < M; m0 += kCP) {
-      const int Mp = min(kCP, M - m0);
+    for (int m0 = 0; m0 < M; m0 += C::CP) {
+      const int Mp = min(C::CP, M - m0);
 #pragma unroll
       for (int u = 0; u < UPT; ++u) {
         const int j = tid + NT * u;
 #pragma unroll
-        for (int c4 = 0; c4 < kCP / 4; ++c4) {
+        for (int c4 = 0; c4 < C::CP / 4; ++c4) {
           float hv[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int m = 4 * c4 + q;
             hv[q] = (m < Mp) ? pool_hidden[(size_t)colsrc[m0 + m] * DH + j] : 0.f;
           }
-          reinterpret_cast<float4*>(XA + (size_t)j * kCP)[c4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          reinterpret_cast<float4*>(XA + (size_t)j * C::CP)[c4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
       }
       named_bar_sync(1, NT);
-      const int nc = (Mp + 3) / 4;
-      if (nc == 1) run_pass<C, 1, true>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean, pool_hidden, bh, b1r, b2r, tid, lane, ph_dummy, tmark_dummy);
-      else if (nc == 2) run_pass<C, 2, true>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean, pool_hidden, bh, b1r, b2r, tid, lane, ph_dummy, tmark_dummy);
-      else if (nc == 3) run_pass<C, 3, true>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean, pool_hidden, bh, b1r, b2r, tid, lane, ph_dummy, tmark_dummy);
-      else run_pass<C, 4, true>(p, ring, full, empty, it, XA, XB, smem_f, cc, m0, Mp, pool_mean, pool_hidden, bh, b1r, b2r, tid, lane, ph_dummy, tmark_dummy);
+      run_pass_any<C, DEEP>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean, pool_hidden, bh, b1r, b2r, tid, lane, ph_dummy, tmark_dummy);
       named_bar_sync(1, NT);
     }
     for (int n = a + tid; n < b; n += NT) {

@@ -1,0 +1,21 @@
+// Kernel launchers, one translation unit per (kernel family, shape group) so that nvcc compiles
+// the heavy template instantiations in parallel (`--threads 0`).  uis_api.cu only sees these.
+#pragma once
+#include <cuda_runtime.h>
+#include "uis_beam.cuh"
+
+namespace uis {
+// each returns false if (H, D) is not one of its shapes; *err receives the CUDA status otherwise
+bool launch_beam_large(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+bool launch_beam_small(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+bool launch_tree_large(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+bool launch_tree_small(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+
+template <class Kern>
+inline cudaError_t launch_with_smem(Kern kern, const BeamParams& p, int ctas, int block, unsigned smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<ctas, block, smem, st>>>(p);
+  return cudaGetLastError();
+}
+}  // namespace uis
