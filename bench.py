@@ -247,9 +247,9 @@ def run_reference(args):
   have_ref = os.path.exists(os.path.join(ROOT, 'baseline', '_ref', 'uisrnn', 'uisrnn.py'))
   kind = 'reference' if have_ref else 'port'
   cores = os.cpu_count() or 1
-  procs = max(1, min(cores, 256))
+  procs = max(1, min(cores, 128))
   # bounded sample: one utterance slice per process and step, sized for ~5-10 s per step
-  n_frames = 40 if kind == 'reference' else N_FRAMES
+  n_frames = 24 if kind == 'reference' else N_FRAMES
   ctx = mp.get_context('spawn')
   times = []
   with ctx.Pool(procs) as pool:
