@@ -173,7 +173,7 @@ int uis_trainer_destroy(uis_trainer* t);
 /* One iteration on one batch = what utils.pack_sequence builds (utils.py:237-246): x_host fp32
  * [L][B][D] zero-padded, time-major, row 0 all zeros; lengths[B] (incl. the zero row) sorted
  * descending with lengths[0] == L; B <= 32.  mode 0: forward + backward + clip + Adam + clamp;
- * mode 1: forward + backward only (for gradient checks).  losses_out[3] (host, may be NULL) =
+ * mode 1: forward + backward only (for gradient checks); mode 2: data-parallel shard (see below).  losses_out[3] (host, may be NULL) =
  * negative log likelihood, sigma2 prior, regularisation -- the three numbers uisrnn.py:297-310 logs.
  * With losses_out == NULL the call only enqueues work on `stream` (the host batch has been staged
  * when it returns); read the losses later with uis_trainer_losses(). */
@@ -185,6 +185,19 @@ int uis_trainer_get(uis_trainer* t, int what, float* const* out);
 
 /* Losses of the last `count` (<= 4096) steps, oldest first: out[count][3] host floats.  Synchronises. */
 int uis_trainer_losses(uis_trainer* t, int count, float* out);
+
+/*
+ * Data-parallel fit() (optional): every rank runs uis_trainer_step(mode = 2) on its
+ * shard of the mini-batch (forward + backward with UN-normalised gradients), exports
+ *   [gradients of parameters 0-8 | per-dimension squared-residual sums | per-dimension counts | row count]
+ * (uis_trainer_comm_size() floats) into a caller-owned DEVICE buffer, all-reduces(sum) it (NCCL over
+ * NVLink: one collective per iteration), and hands it back: uis_trainer_comm_apply() normalises by the
+ * global row count, forms the sigma2 gradient and the three losses from the global statistics, adds the
+ * regulariser, clips and takes the Adam step -- identically on every rank.
+ */
+int64_t uis_trainer_comm_size(uis_trainer* t);
+int uis_trainer_comm_export(uis_trainer* t, float* dev_buf, void* stream);
+int uis_trainer_comm_apply(uis_trainer* t, const float* dev_buf, void* stream);
 
 #ifdef __cplusplus
 }

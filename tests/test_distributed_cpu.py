@@ -49,3 +49,15 @@ def test_predict_sharded_gloo_world2(tmp_path):
   for rank in (0, 1):
     got = np.load(str(tmp_path / ('rank%d.npy' % rank)), allow_pickle=True).tolist()
     assert [list(g) for g in got] == want
+
+
+def test_shard_columns_partition_keeps_length_order():
+  from uisrnn_b200.uisrnn import shard_columns
+  lengths = np.sort(np.random.default_rng(3).integers(2, 90, size=32))[::-1]
+  for world in (1, 2, 3, 8, 40):
+    parts = [shard_columns(32, r, world) for r in range(world)]
+    assert sorted(int(c) for p in parts for c in p) == list(range(32))
+    for p in parts:
+      assert np.all(np.diff(lengths[p]) <= 0)          # every shard is still sorted by decreasing length
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= 1

@@ -415,6 +415,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi;
 }
 
+// g[i] /= nz for i < n  (data-parallel path: gradients were accumulated without the 1/#rows factor)
+__global__ void scale_by_inv_kernel(float* __restrict__ g, const float* __restrict__ nz, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] = g[i] / nz[0];
+}
+
 struct DBuf {
   float* p = nullptr;
   size_t cap = 0;
@@ -481,6 +487,54 @@ struct uis_trainer {
 namespace {
 enum { SEG_WIH = 0, SEG_WHH, SEG_BIH, SEG_BHH, SEG_W1, SEG_B1, SEG_W2, SEG_B2, SEG_H0, SEG_SIGMA2, SEG_COUNT };
 }
+
+namespace {
+
+// Tail of an iteration: regulariser gradient + loss3, then (mode 0) clip + Adam + clamp; records the losses.
+int finish_step(uis_trainer* t, cudaStream_t st, int mode, float* losses_out) {
+  using namespace uis;
+  const int D = t->D;
+  float* P = t->params.p;
+  float* G = t->grads.p;
+  const int* so = t->seg_off_h;
+  float* nz = t->small + 2 * D;
+  float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 16;
+  seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(P, t->seg_off_d, t->partial.p);
+  seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, p_sumsq);
+  {
+    int maxseg = 0;
+    for (int s = 0; s < 8; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
+    dim3 grid((maxseg + 255) / 256, 8);
+    reg_grad_kernel<<<grid, 256, 0, st>>>(P, G, t->seg_off_d, p_sumsq, t->hp.regularization_weight, 8, scalars);
+  }
+  CUT(cudaGetLastError());
+  if (mode == 0) {
+    seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(G, t->seg_off_d, t->partial.p);
+    seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, g_sumsq);
+    t->step += 1;
+    // torch.optim.Adam (defaults): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles
+    const double bc1 = 1.0 - std::pow(0.9, (double)t->step), bc2 = 1.0 - std::pow(0.999, (double)t->step);
+    adam_kernel<<<(t->total + 255) / 256, 256, 0, st>>>(P, G, t->m.p, t->v.p, g_sumsq, 8, t->rnn_end, t->sigma_begin,
+                                                        t->total, t->hp.grad_max_norm,
+                                                        (float)((double)t->hp.learning_rate / bc1),
+                                                        (float)std::sqrt(bc2), t->hp.train_sigma2);
+    CUT(cudaGetLastError());
+  }
+  // loss history on the device: slot (calls mod capacity); losses_out == NULL => fully asynchronous step
+  if (!t->loss_hist.p) {
+    if (int rc = t->loss_hist.ensure(3 * 4096)) return rc;
+    t->hist_cap = 4096;
+  }
+  CUT(cudaMemcpyAsync(t->loss_hist.p + 3 * (t->calls % t->hist_cap), scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  t->calls += 1;
+  if (losses_out) {
+    CUT(cudaMemcpyAsync(losses_out, scalars, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUT(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -640,10 +694,19 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   if (int rc = gemm<false, true>(st, t->sc, t->a1.p, P + so[SEG_W2], P + so[SEG_B2], nullptr, t->mu.p, (int)R, D, H)) return rc;
   const int bd_blocks = (B * D + 255) / 256;
   loss_fwd_kernel<<<bd_blocks, 256, 0, st>>>(t->mu.p, t->x.p, t->diff.p, sum_sq_d, cnt_d, nz, L, B, D);
-  loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
-                                       G + so[SEG_SIGMA2], scalars, D);
+  // mode 2 (data-parallel shard): the row count is global, so gradients are accumulated WITHOUT the 1/nz
+  // factor (they are linear in it) and normalised after the all-reduce, in uis_trainer_comm_apply()
+  const float* nz_for_bwd = nz;
+  if (mode == 2) {
+    const float one = 1.0f;
+    CUT(cudaMemcpyAsync(scalars + 3, &one, sizeof(float), cudaMemcpyHostToDevice, st));
+    nz_for_bwd = scalars + 3;
+  } else {
+    loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
+                                         G + so[SEG_SIGMA2], scalars, D);
+  }
   // ---- backward
-  loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[SEG_SIGMA2], nz, t->dmu.p, L, B, D);
+  loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[SEG_SIGMA2], nz_for_bwd, t->dmu.p, L, B, D);
   CUT(cudaGetLastError());
   if (int rc = gemm<true, false>(st, t->sc, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[SEG_W2], D, H, (int)R)) return rc;
   colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(t->dmu.p, G + so[SEG_B2], (int)R, D);
@@ -668,40 +731,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgi.p, G + so[SEG_BIH], (int)R, 3 * H);
   colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[SEG_BHH], (int)R, 3 * H);
   colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[SEG_H0], B, H);  // d h0 = sum_b d h_{-1}
-  // regulariser gradient + loss3
-  seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(P, t->seg_off_d, t->partial.p);
-  seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, p_sumsq);
-  {
-    int maxseg = 0;
-    for (int s = 0; s < 8; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
-    dim3 grid((maxseg + 255) / 256, 8);
-    reg_grad_kernel<<<grid, 256, 0, st>>>(P, G, t->seg_off_d, p_sumsq, t->hp.regularization_weight, 8, scalars);
-  }
-  CUT(cudaGetLastError());
-  if (mode == 0) {
-    seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(G, t->seg_off_d, t->partial.p);
-    seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, g_sumsq);
-    t->step += 1;
-    // torch.optim.Adam (defaults): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles
-    const double bc1 = 1.0 - std::pow(0.9, (double)t->step), bc2 = 1.0 - std::pow(0.999, (double)t->step);
-    adam_kernel<<<(t->total + 255) / 256, 256, 0, st>>>(P, G, t->m.p, t->v.p, g_sumsq, 8, t->rnn_end, t->sigma_begin,
-                                                        t->total, t->hp.grad_max_norm,
-                                                        (float)((double)t->hp.learning_rate / bc1),
-                                                        (float)std::sqrt(bc2), t->hp.train_sigma2);
-    CUT(cudaGetLastError());
-  }
-  // loss history on the device: slot (calls mod capacity); losses_out == NULL => fully asynchronous step
-  if (!t->loss_hist.p) {
-    if (int rc = t->loss_hist.ensure(3 * 4096)) return rc;
-    t->hist_cap = 4096;
-  }
-  CUT(cudaMemcpyAsync(t->loss_hist.p + 3 * (t->calls % t->hist_cap), scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  t->calls += 1;
-  if (losses_out) {
-    CUT(cudaMemcpyAsync(losses_out, scalars, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUT(cudaStreamSynchronize(st));
-  }
-  return 0;
+  if (mode == 2) return 0;  // gradients + statistics stay on the device for uis_trainer_comm_export()
+  return finish_step(t, st, mode, losses_out);
 }
 
 // Losses of the last `count` (<= 4096) calls to uis_trainer_step, oldest first: out[count][3] (host).  Synchronises.
@@ -715,6 +746,35 @@ int uis_trainer_losses(uis_trainer* t, int count, float* out) {
     CUT(cudaMemcpy(out + 3 * i, t->loss_hist.p + 3 * slot, 3 * sizeof(float), cudaMemcpyDeviceToHost));
   }
   return 0;
+}
+
+// ---- data-parallel fit(): one all-reduce(sum) per iteration over [unnormalised gradients of the RNN
+// parameters and h0 | per-dimension residual sums | per-dimension counts | row count].
+int64_t uis_trainer_comm_size(uis_trainer* t) { return t ? (int64_t)t->sigma_begin + 2 * t->D + 1 : 0; }
+
+int uis_trainer_comm_export(uis_trainer* t, float* dev_buf, void* stream) {
+  if (!t || !dev_buf) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  CUT(cudaSetDevice(t->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUT(cudaMemcpyAsync(dev_buf, t->grads.p, (size_t)t->sigma_begin * 4, cudaMemcpyDeviceToDevice, st));
+  CUT(cudaMemcpyAsync(dev_buf + t->sigma_begin, t->small, (size_t)(2 * t->D + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int uis_trainer_comm_apply(uis_trainer* t, const float* dev_buf, void* stream) {
+  if (!t || !dev_buf) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  CUT(cudaSetDevice(t->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = t->D;
+  CUT(cudaMemcpyAsync(t->grads.p, dev_buf, (size_t)t->sigma_begin * 4, cudaMemcpyDeviceToDevice, st));
+  CUT(cudaMemcpyAsync(t->small, dev_buf + t->sigma_begin, (size_t)(2 * D + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  float* nz = t->small + 2 * D;
+  uis::scale_by_inv_kernel<<<(t->sigma_begin + 255) / 256, 256, 0, st>>>(t->grads.p, nz, t->sigma_begin);
+  uis::loss_scalar_kernel<<<1, 256, 0, st>>>(t->small, t->small + D, nz, t->params.p + t->seg_off_h[SEG_SIGMA2],
+                                            t->hp.sigma_alpha, t->hp.sigma_beta, t->grads.p + t->seg_off_h[SEG_SIGMA2],
+                                            nz + 1, D);
+  CUT(cudaGetLastError());
+  return finish_step(t, st, 0, nullptr);
 }
 
 // what: 0 = parameters, 1 = gradients of the last step.  out[10] host buffers (any may be NULL).

@@ -57,7 +57,8 @@ class Stats(C.Structure):
 EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destroy',
            'uis_model_constants', 'uis_predict', 'uis_predict_device',
            'uis_predict_workspace_bytes', 'uis_get_stats', 'uis_trainer_create',
-           'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get', 'uis_trainer_losses')
+           'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get', 'uis_trainer_losses',
+           'uis_trainer_comm_size', 'uis_trainer_comm_export', 'uis_trainer_comm_apply')
 
 
 class TrainHParams(C.Structure):
@@ -118,6 +119,12 @@ def load_library():
   lib.uis_trainer_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
   lib.uis_trainer_losses.restype = C.c_int
   lib.uis_trainer_losses.argtypes = [C.c_void_p, C.c_int, fp]
+  lib.uis_trainer_comm_size.restype = C.c_int64
+  lib.uis_trainer_comm_size.argtypes = [C.c_void_p]
+  lib.uis_trainer_comm_export.restype = C.c_int
+  lib.uis_trainer_comm_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+  lib.uis_trainer_comm_apply.restype = C.c_int
+  lib.uis_trainer_comm_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
   del ip
   _lib = lib
   return lib
@@ -297,6 +304,24 @@ class NativeTrainer:
     if count:
       _check(self._lib, self._lib.uis_trainer_losses(self._h, count, out.ctypes.data_as(C.POINTER(C.c_float))))
     return out
+
+  def comm_size(self):
+    return int(self._lib.uis_trainer_comm_size(self._h))
+
+  def step_shard(self, rnn_input, lengths, stream=0):
+    """Data-parallel shard: forward + backward with un-normalised gradients (mode 2)."""
+    x = _f32(rnn_input)
+    L, B, D = x.shape
+    lens = np.ascontiguousarray(lengths, dtype=np.int32)
+    _check(self._lib, self._lib.uis_trainer_step(self._h, x.ctypes.data_as(C.c_void_p),
+                                                  lens.ctypes.data_as(C.POINTER(C.c_int32)), B, L, 2, None,
+                                                  C.c_void_p(stream)))
+
+  def comm_export(self, dev_ptr, stream=0):
+    _check(self._lib, self._lib.uis_trainer_comm_export(self._h, C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+  def comm_apply(self, dev_ptr, stream=0):
+    _check(self._lib, self._lib.uis_trainer_comm_apply(self._h, C.c_void_p(dev_ptr), C.c_void_p(stream)))
 
   def step_async(self, rnn_input, lengths, stream=0):
     """Enqueues one full iteration and returns immediately (losses via `losses()`)."""

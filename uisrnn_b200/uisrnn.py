@@ -85,7 +85,12 @@ class UISRNN:
 
   def __init__(self, args):
     self.observation_dim = args.observation_dim
-    self.device = torch.device('cuda:0' if (torch.cuda.is_available() and args.enable_cuda) else 'cpu')
+    # uisrnn.py:97-98 pins 'cuda:0'; here it is the process's CURRENT device (0 unless the caller ran
+    # torch.cuda.set_device, as one-process-per-GPU launches do)
+    if torch.cuda.is_available() and args.enable_cuda:
+      self.device = torch.device('cuda', torch.cuda.current_device())
+    else:
+      self.device = torch.device('cpu')
     self.rnn_model = CoreRNN(self.observation_dim, args.rnn_hidden_size, args.rnn_depth,
                              self.observation_dim, args.rnn_dropout).to(self.device)
     self.rnn_init_hidden = nn.Parameter(torch.zeros(args.rnn_depth, 1, args.rnn_hidden_size).to(self.device))
@@ -172,6 +177,8 @@ class UISRNN:
 
     self.rnn_model.train()
     optimizer = self._get_optimizer(optimizer=args.optimizer, learning_rate=args.learning_rate)
+    if self._native_fit_supported(args):
+      self._sync_replicas()
     sub_sequences, seq_lengths = utils.resize_sequence(
         sequence=train_sequence, cluster_id=train_cluster_id, num_permutations=args.num_permutations)
     if self._native_fit_supported(args):
@@ -213,6 +220,23 @@ class UISRNN:
     self._native = None
     self.logger.print(1, 'Done training with {} iterations'.format(args.train_iteration))
 
+  def _sync_replicas(self):
+    """Data-parallel fit(): inside an initialised `torch.distributed` job every rank adopts rank 0's
+    parameters and host RNG state (numpy + `random`), so the shuffle of `concatenate_training_data`, the
+    permutations of `resize_sequence` and every mini-batch draw are the same on all ranks.  No-op in a
+    single process."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+      return
+    with torch.no_grad():
+      for tensor in list(self.rnn_model.state_dict().values()) + [self.rnn_init_hidden.data, self.sigma2.data]:
+        dist.broadcast(tensor, src=0)
+    import random
+    rng = [np.random.get_state(), random.getstate()]  # utils.py draws from both generators
+    dist.broadcast_object_list(rng, src=0)
+    np.random.set_state(rng[0])
+    random.setstate(rng[1])
+
   def _native_fit_supported(self, args):
     """The hand-written training kernels (csrc/uis_train.cu) cover the default model family:
     CUDA device, one GRU layer, mini-batches of 1..32 sequences.  Other configurations train with
@@ -227,6 +251,11 @@ class UISRNN:
     gradients and Adam state stay on the device; per iteration only the batch goes up and three
     loss scalars come back."""
     from . import native
+    import torch.distributed as dist
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    # world > 1: data-parallel fit (SURVEY 8(e), optional) -- every rank holds rank 0's parameters and draws
+    # the SAME mini-batches (_sync_replicas); rank r owns batch columns r, r + world, ...
     state = {k: v.detach().cpu().numpy() for k, v in self.rnn_model.state_dict().items()}
     params = {name: state[name] for name in native.PARAM_ORDER[:8]}
     params['rnn_init_hidden'] = self.rnn_init_hidden.detach().cpu().numpy().reshape(-1)
@@ -236,12 +265,26 @@ class UISRNN:
                'train_sigma2': self.estimate_sigma2}
     trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
     self.last_training_losses = []
+    comm = torch.zeros(trainer.comm_size(), dtype=torch.float32, device=self.device) if world > 1 else None
     try:
       pending = 0  # steps enqueued since the losses were last read back
       for num_iter in range(args.train_iteration):
         # the device works on iteration i while the host packs the batch of iteration i + 1
         rnn_input, lengths = utils.pack_batch(sub_sequences, seq_lengths, args.batch_size, self.observation_dim)
-        trainer.step_async(rnn_input.astype(np.float32), lengths)
+        if world == 1:
+          trainer.step_async(rnn_input.astype(np.float32), lengths)
+        else:
+          # local forward/backward on this rank's columns -> ONE all-reduce(sum) of [gradients | loss
+          # statistics] over NCCL -> identical normalise / clip / Adam step on every rank
+          mine = shard_columns(len(lengths), rank, world)
+          if len(mine):
+            local_lengths = lengths[mine]
+            trainer.step_shard(rnn_input[:local_lengths[0], mine, :].astype(np.float32), local_lengths)
+            trainer.comm_export(comm.data_ptr())
+          else:
+            comm.zero_()
+          dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+          trainer.comm_apply(comm.data_ptr())
         pending += 1
         log_now = num_iter % 10 == 0 or num_iter == args.train_iteration - 1
         if log_now or pending == 4096:
@@ -278,6 +321,8 @@ class UISRNN:
       train_cluster_ids = [train_cluster_ids]
     elif not isinstance(train_sequences, list):
       raise TypeError('train_sequences must be a list or numpy.ndarray')
+    if self._native_fit_supported(args):
+      self._sync_replicas()  # before the shuffle inside concatenate_training_data
     if self.estimate_transition_bias:
       bias, denominator = utils.estimate_transition_bias(train_cluster_ids)
       if self.transition_bias is None:
@@ -432,6 +477,12 @@ class _DeviceTwin:
 def _clone_for_device(model, device_index):
   del device_index
   return _DeviceTwin(model.export_weights())
+
+
+def shard_columns(width, rank, world):
+  """Columns of a (length-sorted) mini-batch owned by `rank` in data-parallel fit(): rank, rank + world,
+  ... -- every shard stays sorted by decreasing length and the long sequences are spread evenly."""
+  return np.arange(rank, width, world)
 
 
 def shard_by_frames(lengths, n_shards):
