@@ -187,6 +187,20 @@ int uis_trainer_get(uis_trainer* t, int what, float* const* out);
 int uis_trainer_losses(uis_trainer* t, int count, float* out);
 
 /*
+ * Training set resident on the device (replaces the per-iteration host work of
+ * utils.pack_sequence, utils.py:204-250, and the num_permutations-fold float64 copy of
+ * utils.resize_sequence, utils.py:172-201).  rows: host float64 [n_rows][D] = the concatenated training
+ * sequence (cast to fp32 on the device); index: host int32 [n_index] = the row indices of every
+ * sub-sequence back to back; offsets: host int64 [n_sub + 1].  uis_trainer_step_corpus() then runs one
+ * iteration on the batch whose columns are sub-sequences chosen[0..B) (the caller keeps the reference's RNG
+ * draw and passes the ids in pack_sequence's column order: lengths descending); the batch tensor is
+ * gathered on the device, zero frame first, zero padded.
+ */
+int uis_trainer_set_corpus(uis_trainer* t, const double* rows, int64_t n_rows, const int32_t* index, int64_t n_index,
+                           const int64_t* offsets, int32_t n_sub);
+int uis_trainer_step_corpus(uis_trainer* t, const int32_t* chosen, int B, int mode, float* losses_out, void* stream);
+
+/*
  * Data-parallel fit() (optional): every rank runs uis_trainer_step(mode = 2) on its
  * shard of the mini-batch (forward + backward with UN-normalised gradients), exports
  *   [gradients of parameters 0-8 | per-dimension squared-residual sums | per-dimension counts | row count]

@@ -175,3 +175,56 @@ def test_fit_api_uses_native_trainer_and_learns():
   x, truth = synth_utt(6100, n_frames=80, dim=64, n_spk=3, noise=0.08)
   acc = uisrnn.compute_sequence_match_accuracy(model.predict(x, i), truth.tolist())
   assert acc > 0.9
+
+
+def test_device_gathered_batch_equals_host_packed_batch():
+  """uis_trainer_step_corpus (training set resident on the device, batch gathered there) is bit-identical
+  to uis_trainer_step on the batch utils.pack_batch builds on the host."""
+  from uisrnn_b200 import utils
+  from uisrnn_b200.synth import synth_training_set
+  model, targs, _, _ = _model_and_data(seed=17)
+  seqs, ids = synth_training_set(4000, 30, n_frames=50, dim=64, n_spk=3, noise=0.08)
+  x, y = utils.concatenate_training_data(seqs, ids, True, True)
+  np.random.seed(23)
+  subs, lens = utils.resize_sequence(x, np.array(y), targs.num_permutations)
+  np.random.seed(23)
+  index_lists, lens2 = utils.resize_indices(np.array(y), targs.num_permutations)
+  assert lens == lens2
+  host, dev = _native_trainer(model, targs), _native_trainer(model, targs)
+  dev.set_corpus(x, index_lists)
+  sampler = utils.BatchSampler(lens, targs.batch_size)
+  for it in range(5):
+    np.random.seed(100 + it)
+    batch, lengths = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+    np.random.seed(100 + it)
+    chosen, lengths2 = sampler.draw()
+    assert np.array_equal(lengths, lengths2)
+    want = host.step(batch.astype(np.float32), lengths)
+    got = dev.step_corpus(chosen, want_losses=True)
+    # same arithmetic on the same rows; the per-dimension loss sums use float atomics (order not fixed)
+    assert np.allclose(got, want, rtol=2e-6, atol=0), (it, got, want)
+  a, b = host.parameters(), dev.parameters()
+  assert all(np.max(np.abs(a[k] - b[k])) < 1e-6 for k in a)
+  with pytest.raises(Exception):
+    dev.step_corpus(np.array([len(index_lists)]))   # id out of range
+  host.close(); dev.close()
+
+
+def test_persistent_recurrence_kernels_match_per_step_launches(monkeypatch):
+  """The cooperative whole-sequence GRU kernels (one launch per direction) against the per-step launches
+  (UISRNN_B200_TRAIN_STEPWISE=1): same losses and gradients up to fp32 summation order."""
+  from uisrnn_b200 import utils
+  model, targs, subs, lens = _model_and_data(seed=19)
+  np.random.seed(7)
+  batch, lengths = utils.pack_batch(subs, lens, targs.batch_size, model.observation_dim)
+  persistent = _native_trainer(model, targs)
+  want_losses = persistent.step(batch.astype(np.float32), lengths, grads_only=True)
+  want = persistent.gradients()
+  monkeypatch.setenv('UISRNN_B200_TRAIN_STEPWISE', '1')
+  stepwise = _native_trainer(model, targs)
+  got_losses = stepwise.step(batch.astype(np.float32), lengths, grads_only=True)
+  got = stepwise.gradients()
+  assert np.allclose(got_losses, want_losses, rtol=1e-5)
+  for name in want:
+    assert _rel(got[name], want[name]) < 2e-5, name
+  persistent.close(); stepwise.close()

@@ -181,3 +181,29 @@ def test_sigma2_prior_and_regularization():
   assert torch.allclose(loss_func.sigma2_prior_loss(n, 1.0, 3.0, s2), want)
   ps = [torch.ones(3), torch.full((2, 2), 2.0)]
   assert torch.allclose(loss_func.regularization_loss(ps, 0.1), torch.tensor(0.1 * (3 ** 0.5 + 4.0)))
+
+
+def test_resize_indices_and_batch_sampler_mirror_the_data_path():
+  """The device-resident training path replaces sub-sequence copies by row indices and the packed batch
+  by the ids of its columns: same RNG stream, same rows."""
+  from uisrnn_b200 import utils
+  rng = np.random.default_rng(0)
+  ids = np.array(['%d' % v for v in np.repeat(rng.integers(0, 7, 60), rng.integers(1, 9, 60))])
+  seq = rng.normal(size=(len(ids), 5))
+  for perms in (None, 1, 4):
+    np.random.seed(3)
+    subs, lens_a = utils.resize_sequence(seq, ids, perms)
+    np.random.seed(3)
+    index_lists, lens_b = utils.resize_indices(ids, perms)
+    assert lens_a == lens_b
+    assert all(np.array_equal(x, seq[ix]) for x, ix in zip(subs, index_lists))
+    np.random.seed(5)
+    x, lengths = utils.pack_batch(subs, lens_a, 6, 5)
+    state_after_pack = np.random.get_state()[1].copy()
+    np.random.seed(5)
+    chosen, lengths2 = utils.BatchSampler(lens_a, 6).draw()
+    assert np.array_equal(state_after_pack, np.random.get_state()[1])   # consumed the same random numbers
+    assert np.array_equal(lengths, lengths2)
+    for column, k in enumerate(chosen):
+      assert np.array_equal(x[1:lengths[column], column, :], subs[k])
+      assert not x[0, column].any() and not x[lengths[column]:, column].any()

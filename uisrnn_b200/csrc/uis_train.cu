@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -239,6 +240,191 @@ __global__ void gru_gate_fwd_kernel(const float* __restrict__ gh, const float* _
   r_t[q] = r; z_t[q] = z; n_t[q] = n; hn_t[q] = hn;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent recurrence kernels (one cooperative launch per direction instead of two launches per time step).
+// The sequential part of an iteration is L dependent products with W_hh (3 MB) on <= 32 rows: far too little
+// work per step for a launch each (a launch + drain costs more than the step's arithmetic).  Here CTA c owns
+// kUPC = 4 hidden units for the whole sequence -- the 12 rows (forward) / 4 columns (backward) of W_hh it
+// needs stay in its shared memory (24 KB) for all L steps -- and the CTAs exchange h_t (forward) / dGh_t
+// (backward) through L2 with one grid-wide barrier per step.  H % 128 == 0, H / 4 CTAs (128 at H = 512).
+constexpr int kUPC = 4;
+struct SeqParams { int length[32]; int L, B, H; };
+
+__device__ __forceinline__ int seq_rows_alive(const SeqParams& sp, int t) {
+  int nb = 0;
+  for (int b = 0; b < sp.B; ++b) nb += sp.length[b] > t ? 1 : 0;
+  return nb;
+}
+
+// All CTAs arrive; returns when `target` arrivals are visible.  Bounded spin: a lost CTA sets *err instead of
+// hanging the device (the launch is cooperative, so co-residency is guaranteed and this never fires).
+__device__ __forceinline__ void seq_grid_sync(unsigned* bar, unsigned target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v = 0;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target && ++spins < (1ll << 24));
+    if (v < target) atomicExch(err, 1);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Forward: for t = 0..L-1, rows b < nb(t):  gh = W_hh h_{t-1};  (r, z, n, h_t) as gru_gate_fwd_kernel.
+// hs: [(L+1)*B][H] with hs[0..B) = h_{-1};  gi: [L*B][3H] = W_ih x + b_ih.
+__global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restrict__ whh, const float* __restrict__ bhh,
+                                                          const float* __restrict__ gi, float* hs,
+                                                          float* __restrict__ r_o, float* __restrict__ z_o,
+                                                          float* __restrict__ n_o, float* __restrict__ hn_o,
+                                                          SeqParams sp, unsigned* bar, int* err) {
+  extern __shared__ float4 seq_smem[];
+  const int H = sp.H, B = sp.B, S = H + 4, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float* sW = reinterpret_cast<float*>(seq_smem);  // [3 * kUPC][H]: row g * kUPC + u = W_hh[g * H + j0 + u][:]
+  float* sh = sW + 3 * kUPC * H;                   // [32][H + 4]
+  float* sred = sh + 32 * S;                       // [8][3 * kUPC][32]
+  const int j0 = blockIdx.x * kUPC, H4 = H / 4, kslice = H / 8;
+  for (int i = tid; i < 3 * kUPC * H4; i += 256) {
+    const int row = i / H4, k4 = i % H4, g = row / kUPC, u = row % kUPC;
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(whh + (size_t)(g * H + j0 + u) * H)[k4];
+  }
+  __syncthreads();
+  for (int t = 0; t < sp.L; ++t) {
+    const int nb = seq_rows_alive(sp, t);
+    if (nb == 0) break;
+    const size_t o = (size_t)t * B;
+    for (int i = tid; i < nb * H4; i += 256) {  // h_{t-1}, written by every CTA in the previous step: read through L2
+      const int b = i / H4, k4 = i % H4;
+      *reinterpret_cast<float4*>(sh + b * S + 4 * k4) = __ldcg(reinterpret_cast<const float4*>(hs + (o + b) * H) + k4);
+    }
+    __syncthreads();
+    float acc[3 * kUPC];
+#pragma unroll
+    for (int q = 0; q < 3 * kUPC; ++q) acc[q] = 0.f;
+    if (lane < nb) {
+      const float* hb = sh + lane * S + w * kslice;
+      const float* wb = sW + w * kslice;
+      for (int k = 0; k < kslice; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + k);
+#pragma unroll
+        for (int q = 0; q < 3 * kUPC; ++q) {
+          const float4 wv = *reinterpret_cast<const float4*>(wb + q * H + k);
+          acc[q] = fmaf(wv.x, hv.x, acc[q]); acc[q] = fmaf(wv.y, hv.y, acc[q]);
+          acc[q] = fmaf(wv.z, hv.z, acc[q]); acc[q] = fmaf(wv.w, hv.w, acc[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3 * kUPC; ++q) sred[(w * 3 * kUPC + q) * 32 + lane] = acc[q];
+    __syncthreads();
+    if (tid < 32 * kUPC) {
+      const int b = tid & 31, u = tid >> 5, j = j0 + u;
+      if (b < nb) {
+        float g3[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float a = 0.f;
+          for (int ww = 0; ww < 8; ++ww) a += sred[(ww * 3 * kUPC + g * kUPC + u) * 32 + b];
+          g3[g] = a;
+        }
+        const float* gir = gi + (o + b) * 3 * H;
+        const float r = sigmoid_f32(gir[j] + (g3[0] + bhh[j]));
+        const float z = sigmoid_f32(gir[H + j] + (g3[1] + bhh[H + j]));
+        const float hn = g3[2] + bhh[2 * H + j];
+        const float n = tanhf(gir[2 * H + j] + r * hn);
+        const float hp = sh[b * S + j];
+        const size_t q = (o + b) * H + j;
+        hs[q + (size_t)B * H] = (hp - n) * z + n;
+        r_o[q] = r; z_o[q] = z; n_o[q] = n; hn_o[q] = hn;
+      }
+    }
+    seq_grid_sync(bar, (unsigned)(t + 1) * gridDim.x, err);
+  }
+}
+
+// Backward: for t = L-1..0, rows b < nb(t): dh = dout_t + carry; gate gradients -> dGi_t, dGh_t (as
+// gru_bwd_step_kernel); carry = dh * z + dGh_t W_hh.  The CTA keeps the carry of its own 4 units on chip.
+__global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restrict__ whh, const float* __restrict__ dout,
+                                                          const float* __restrict__ r_i, const float* __restrict__ z_i,
+                                                          const float* __restrict__ n_i, const float* __restrict__ hn_i,
+                                                          const float* __restrict__ hs, float* __restrict__ dgi,
+                                                          float* dgh, float* __restrict__ carry_out, SeqParams sp,
+                                                          unsigned* bar, int* err) {
+  extern __shared__ float4 seq_smem[];
+  const int H = sp.H, B = sp.B, H3 = 3 * H, CH = H3 / 4, S = CH + 4, rpw = CH / 8;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, j0 = blockIdx.x * kUPC;
+  float4* sWT = seq_smem;                                 // [3H]: W_hh[row][j0 .. j0 + 3]
+  float* sg = reinterpret_cast<float*>(sWT + H3);         // [32][CH + 4]
+  float4* sred = reinterpret_cast<float4*>(sg + 32 * S);  // [8][32]
+  float* scarry = reinterpret_cast<float*>(sred + 8 * 32);  // [32][4]
+  for (int i = tid; i < H3; i += 256) sWT[i] = *reinterpret_cast<const float4*>(whh + (size_t)i * H + j0);
+  if (tid < 32 * kUPC) scarry[tid] = 0.f;
+  __syncthreads();
+  unsigned epoch = 0;
+  for (int t = sp.L - 1; t >= 0; --t) {
+    const int nb = seq_rows_alive(sp, t);
+    if (nb == 0) continue;
+    const size_t o = (size_t)t * B;
+    if (tid < 32 * kUPC) {
+      const int b = tid >> 2, u = tid & 3, j = j0 + u;
+      if (b < nb) {
+        const size_t q = (o + b) * H + j;
+        const float dh = dout[q] + scarry[tid];
+        const float r = r_i[q], z = z_i[q], n = n_i[q], hn = hn_i[q], hp = hs[q];
+        const float dn = dh * (1.f - z), dz = dh * (hp - n);
+        const float dan = dn * (1.f - n * n);
+        const float dar = dan * hn * r * (1.f - r);
+        const float daz = dz * z * (1.f - z);
+        float* gi = dgi + (o + b) * H3;
+        float* gh = dgh + (o + b) * H3;
+        gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
+        gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = dan * r;
+        scarry[tid] = dh * z;
+      }
+    }
+    seq_grid_sync(bar, ++epoch * gridDim.x, err);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < H3; c0 += CH) {
+      for (int i = tid; i < nb * (CH / 4); i += 256) {  // dGh_t, written by every CTA before the barrier
+        const int b = i / (CH / 4), c4 = i % (CH / 4);
+        *reinterpret_cast<float4*>(sg + b * S + 4 * c4) = __ldcg(reinterpret_cast<const float4*>(dgh + (o + b) * H3 + c0) + c4);
+      }
+      __syncthreads();
+      if (lane < nb) {
+        const float* gb = sg + lane * S + w * rpw;
+        const float4* wt = sWT + c0 + w * rpw;
+        for (int rr = 0; rr < rpw; rr += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gb + rr);
+          const float4 w0 = wt[rr], w1 = wt[rr + 1], w2 = wt[rr + 2], w3 = wt[rr + 3];
+          acc.x = fmaf(g4.x, w0.x, acc.x); acc.y = fmaf(g4.x, w0.y, acc.y); acc.z = fmaf(g4.x, w0.z, acc.z); acc.w = fmaf(g4.x, w0.w, acc.w);
+          acc.x = fmaf(g4.y, w1.x, acc.x); acc.y = fmaf(g4.y, w1.y, acc.y); acc.z = fmaf(g4.y, w1.z, acc.z); acc.w = fmaf(g4.y, w1.w, acc.w);
+          acc.x = fmaf(g4.z, w2.x, acc.x); acc.y = fmaf(g4.z, w2.y, acc.y); acc.z = fmaf(g4.z, w2.z, acc.z); acc.w = fmaf(g4.z, w2.w, acc.w);
+          acc.x = fmaf(g4.w, w3.x, acc.x); acc.y = fmaf(g4.w, w3.y, acc.y); acc.z = fmaf(g4.w, w3.z, acc.z); acc.w = fmaf(g4.w, w3.w, acc.w);
+        }
+      }
+      __syncthreads();
+    }
+    sred[w * 32 + lane] = acc;
+    __syncthreads();
+    if (tid < 32 * kUPC) {
+      const int b = tid >> 2, u = tid & 3;
+      if (b < nb) {
+        float a = 0.f;
+        for (int ww = 0; ww < 8; ++ww) a += reinterpret_cast<const float*>(sred + ww * 32 + b)[u];
+        scarry[tid] += a;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 32 * kUPC) {
+    const int b = tid >> 2, u = tid & 3;
+    if (b < B) carry_out[(size_t)b * H + j0 + u] = scarry[tid];
+  }
+}
+
 // out[c][r] = in[r][c]
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cn) {
   __shared__ float tile[32][33];
@@ -421,6 +607,25 @@ __global__ void scale_by_inv_kernel(float* __restrict__ g, const float* __restri
   if (i < n) g[i] = g[i] / nz[0];
 }
 
+// Corpus path (fit() host data prep on the device): the training set lives on the device as
+// fp32 rows; a mini-batch is a gather.  x[t][b][:] = 0 for t = 0 (the prepended zero frame, utils.py:243) and
+// for t >= length_b (padding), else rows[index[begin_b + t - 1]][:].
+struct GatherCols { long long begin[32]; int length[32]; };
+__global__ void gather_batch_kernel(const float* __restrict__ rows, const int* __restrict__ index, GatherCols cols,
+                                    float* __restrict__ x, int L, int B, int D) {
+  const int tb = blockIdx.x;  // t * B + b
+  const int tt = tb / B, b = tb % B;
+  float* dst = x + (size_t)tb * D;
+  const bool live = tt >= 1 && tt < cols.length[b];
+  const float* src = live ? rows + (size_t)index[cols.begin[b] + tt - 1] * D : nullptr;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = live ? src[i] : 0.f;
+}
+__global__ void cast_rows_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __double2float_rn(in[i]);  // = torch .float() of a float64 array
+}
+
 struct DBuf {
   float* p = nullptr;
   size_t cap = 0;
@@ -482,6 +687,13 @@ struct uis_trainer {
   size_t pin_cap = 0;
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   int pin_idx = 0;
+  // corpus path: training rows (fp32) + flat gather indices + per-sub-sequence offsets (host copy)
+  unsigned* seq_bar = nullptr;  // [2] arrival counters of the persistent recurrence kernels; [2] = error flag
+  int seq_mode = -1;            // -1 unknown, 0 per-step launches, 1 persistent cooperative kernels
+  uis::DBuf corpus;
+  int* corpus_index = nullptr;
+  long long corpus_rows = 0;
+  std::vector<long long> sub_off;
 };
 
 namespace {
@@ -590,6 +802,9 @@ int uis_trainer_destroy(uis_trainer* t) {
   if (t->small) cudaFree(t->small);
   if (t->tickets) cudaFree(t->tickets);
   if (t->gemm_tickets) cudaFree(t->gemm_tickets);
+  if (t->corpus_index) cudaFree(t->corpus_index);
+  if (t->seq_bar) cudaFree(t->seq_bar);
+  t->corpus.release();
   for (int i = 0; i < 2; ++i) {
     if (t->pin[i]) cudaFreeHost(t->pin[i]);
     if (t->pin_ev[i]) cudaEventDestroy(t->pin_ev[i]);
@@ -598,21 +813,124 @@ int uis_trainer_destroy(uis_trainer* t) {
   return 0;
 }
 
-// One iteration.  x_host: fp32 [L][B][D] zero-padded batch (row 0 = zero frame), lengths[B] sorted
-// descending (each includes the zero frame).  mode 0: full step (forward, backward, clip, Adam);
-// mode 1: forward + backward only (gradients can be read back with uis_trainer_get, for tests).
-int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
-                     float* losses_out /*[3] host*/, void* stream) {
-  using namespace uis;
-  if (!t || !x_host || !lengths) return api_fail(UIS_ERR_INVALID, "null argument");
-  if (B < 1 || B > 32) return api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
-  if (L < 2) return api_fail(UIS_ERR_INVALID, "L < 2");
+namespace {
+size_t seq_fwd_smem(int H) { return (size_t)(3 * uis::kUPC * H + 32 * (H + 4) + 8 * 3 * uis::kUPC * 32) * 4; }
+size_t seq_bwd_smem(int H) { return (size_t)3 * H * 16 + (size_t)32 * (3 * H / 4 + 4) * 4 + 8 * 32 * 16 + 32 * uis::kUPC * 4; }
+
+// Decides once per trainer whether the persistent recurrence kernels can run (H % 128 == 0, the H / 4 CTAs
+// co-resident, cooperative launch supported); UISRNN_B200_TRAIN_STEPWISE=1 forces the per-step launches.
+int seq_setup(uis_trainer* t) {
+  t->seq_mode = 0;
+  const char* env = std::getenv("UISRNN_B200_TRAIN_STEPWISE");
+  if (env && env[0] == '1') return 0;
+  const int H = t->H;
+  if (H % 128 != 0) return 0;
+  int coop = 0, sms = 0, max_smem = 0;
+  CUT(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, t->device));
+  CUT(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
+  CUT(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, t->device));
+  if (!coop || seq_fwd_smem(H) > (size_t)max_smem || seq_bwd_smem(H) > (size_t)max_smem) return 0;
+  CUT(cudaFuncSetAttribute(uis::gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_fwd_smem(H)));
+  CUT(cudaFuncSetAttribute(uis::gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_bwd_smem(H)));
+  int occ_f = 0, occ_b = 0;
+  CUT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, uis::gru_seq_fwd_kernel, 256, seq_fwd_smem(H)));
+  CUT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, uis::gru_seq_bwd_kernel, 256, seq_bwd_smem(H)));
+  if (occ_f * sms < H / uis::kUPC || occ_b * sms < H / uis::kUPC) return 0;
+  CUT(cudaMalloc(&t->seq_bar, 4 * sizeof(unsigned)));
+  CUT(cudaMemset(t->seq_bar, 0, 4 * sizeof(unsigned)));
+  t->seq_mode = 1;
+  return 0;
+}
+
+int check_lengths(const int32_t* lengths, int B, int L) {
+  if (B < 1 || B > 32) return uis::api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
+  if (L < 2) return uis::api_fail(UIS_ERR_INVALID, "L < 2");
   for (int b = 0; b < B; ++b) {
     if (lengths[b] < 1 || lengths[b] > L || (b > 0 && lengths[b] > lengths[b - 1]) || (b == 0 && lengths[0] != L))
-      return api_fail(UIS_ERR_INVALID, "lengths must be sorted descending with lengths[0] == L");
+      return uis::api_fail(UIS_ERR_INVALID, "lengths must be sorted descending with lengths[0] == L");
   }
+  return 0;
+}
+int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode, float* losses_out, cudaStream_t st,
+                  const float* x_host, const uis::GatherCols* cols);
+}  // namespace
+
+// One iteration on a host batch.  x_host: fp32 [L][B][D] zero-padded (row 0 = zero frame), lengths[B] sorted
+// descending (each includes the zero frame).
+int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
+                     float* losses_out /*[3] host*/, void* stream) {
+  if (!t || !x_host || !lengths) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  if (int rc = check_lengths(lengths, B, L)) return rc;
   CUT(cudaSetDevice(t->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return run_iteration(t, lengths, B, L, mode, losses_out, static_cast<cudaStream_t>(stream), x_host, nullptr);
+}
+
+// Training set on the device: rows [n_rows][D] float64 host (cast to fp32 on the device, as the reference's
+// torch.from_numpy(...).float() does per batch, utils.py:245), index = the concatenated row indices of every
+// sub-sequence of utils.resize_sequence, offsets[n_sub + 1] its prefix sums.
+int uis_trainer_set_corpus(uis_trainer* t, const double* rows, int64_t n_rows, const int32_t* index, int64_t n_index,
+                           const int64_t* offsets, int32_t n_sub) {
+  if (!t || !rows || !index || !offsets) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  if (n_rows < 1 || n_sub < 1 || n_index < 0 || offsets[0] != 0 || offsets[n_sub] != n_index)
+    return uis::api_fail(UIS_ERR_INVALID, "inconsistent corpus sizes");
+  for (int64_t i = 0; i < n_index; ++i)
+    if (index[i] < 0 || index[i] >= n_rows) return uis::api_fail(UIS_ERR_INVALID, "corpus index out of range");
+  for (int32_t k = 0; k < n_sub; ++k)
+    if (offsets[k + 1] < offsets[k]) return uis::api_fail(UIS_ERR_INVALID, "corpus offsets must be non-decreasing");
+  CUT(cudaSetDevice(t->device));
+  const size_t n = (size_t)n_rows * t->D;
+  if (int rc = t->corpus.ensure(n)) return rc;
+  double* tmp = nullptr;
+  const size_t chunk_rows = std::min<size_t>((size_t)n_rows, (size_t)1 << 16);
+  CUT(cudaMalloc(&tmp, chunk_rows * t->D * sizeof(double)));
+  for (size_t r0 = 0; r0 < (size_t)n_rows; r0 += chunk_rows) {
+    const size_t nr = std::min(chunk_rows, (size_t)n_rows - r0), ne = nr * t->D;
+    cudaError_t e = cudaMemcpy(tmp, rows + r0 * t->D, ne * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      uis::cast_rows_kernel<<<1024, 256>>>(tmp, t->corpus.p + r0 * t->D, ne);
+      e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) { cudaFree(tmp); return uis::api_fail(UIS_ERR_CUDA, "corpus upload: %s", cudaGetErrorString(e)); }
+  }
+  cudaFree(tmp);
+  if (t->corpus_index) { cudaFree(t->corpus_index); t->corpus_index = nullptr; }
+  CUT(cudaMalloc(&t->corpus_index, std::max<size_t>(1, (size_t)n_index) * sizeof(int)));
+  CUT(cudaMemcpy(t->corpus_index, index, (size_t)n_index * sizeof(int), cudaMemcpyHostToDevice));
+  t->corpus_rows = n_rows;
+  t->sub_off.assign(offsets, offsets + n_sub + 1);
+  return 0;
+}
+
+// One iteration on the batch whose columns are sub-sequences chosen[0..B) of the corpus (lengths + 1 sorted
+// descending, as utils.pack_sequence orders them).  Nothing but `chosen` crosses the bus.
+int uis_trainer_step_corpus(uis_trainer* t, const int32_t* chosen, int B, int mode, float* losses_out, void* stream) {
+  if (!t || !chosen) return uis::api_fail(UIS_ERR_INVALID, "null argument");
+  if (t->sub_off.empty()) return uis::api_fail(UIS_ERR_INVALID, "uis_trainer_set_corpus has not been called");
+  if (B < 1 || B > 32) return uis::api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
+  uis::GatherCols cols{};
+  int32_t lengths[32];
+  const long long n_sub = (long long)t->sub_off.size() - 1;
+  for (int b = 0; b < B; ++b) {
+    if (chosen[b] < 0 || chosen[b] >= n_sub) return uis::api_fail(UIS_ERR_INVALID, "sub-sequence id out of range");
+    cols.begin[b] = t->sub_off[chosen[b]];
+    lengths[b] = (int32_t)(t->sub_off[chosen[b] + 1] - t->sub_off[chosen[b]]) + 1;  // + the zero frame
+    cols.length[b] = lengths[b];
+  }
+  if (int rc = check_lengths(lengths, B, lengths[0])) return rc;
+  CUT(cudaSetDevice(t->device));
+  return run_iteration(t, lengths, B, lengths[0], mode, losses_out, static_cast<cudaStream_t>(stream), nullptr, &cols);
+}
+
+}  // extern "C"
+
+namespace {
+// One iteration.  The batch comes either from the host (x_host: fp32 [L][B][D] zero-padded, row 0 = zero frame)
+// or from the device-resident corpus (cols).  lengths[B] sorted descending (each includes the zero frame).
+// mode 0: full step (forward, backward, clip, Adam); mode 1: forward + backward only (gradients can be read
+// back with uis_trainer_get, for tests); mode 2: data-parallel shard.
+int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode, float* losses_out, cudaStream_t st,
+                  const float* x_host, const uis::GatherCols* cols) {
+  using namespace uis;
   const int D = t->D, H = t->H;
   const size_t R = (size_t)L * B;
   if (int rc = t->x.ensure(R * D)) return rc;
@@ -641,10 +959,14 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   const int* so = t->seg_off_h;
   float* sum_sq_d = t->small; float* cnt_d = t->small + D; float* nz = t->small + 2 * D;
   float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 16;
+  (void)p_sumsq; (void)g_sumsq;
   std::vector<int> nb(L);
   for (int tt = 0; tt < L; ++tt) { int c = 0; while (c < B && lengths[c] > tt) ++c; nb[tt] = c; }
 
-  {  // stage the batch in pinned memory: the H2D copy then overlaps the previous iteration's kernels
+  if (cols) {
+    gather_batch_kernel<<<(unsigned)R, 128, 0, st>>>(t->corpus.p, t->corpus_index, *cols, t->x.p, L, B, D);
+    CUT(cudaGetLastError());
+  } else {  // stage the batch in pinned memory: the H2D copy then overlaps the previous iteration's kernels
     const size_t bytes = R * D * 4;
     if (bytes > t->pin_cap) {
       for (int i = 0; i < 2; ++i) {
@@ -675,18 +997,32 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
 
   // ---- forward
   if (int rc = gemm<false, true>(st, t->sc, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
-  {  // k-major copy of W_hh for the recurrent products (the weights change every iteration)
+  if (t->seq_mode < 0) {
+    if (int rc = seq_setup(t)) return rc;
+  }
+  SeqParams sp{};
+  for (int b = 0; b < 32; ++b) sp.length[b] = b < B ? lengths[b] : 0;
+  sp.L = L; sp.B = B; sp.H = H;
+  if (t->seq_mode == 1) {
+    CUT(cudaMemsetAsync(t->seq_bar, 0, 2 * sizeof(unsigned), st));
+    const float* a_whh = P + so[SEG_WHH]; const float* a_bhh = P + so[SEG_BHH]; const float* a_gi = t->gi.p;
+    float* a_hs = t->hs.p; float* a_r = t->r.p; float* a_z = t->z.p; float* a_n = t->n.p; float* a_hn = t->hn.p;
+    unsigned* a_bar = t->seq_bar; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
+    void* args[] = {&a_whh, &a_bhh, &a_gi, &a_hs, &a_r, &a_z, &a_n, &a_hn, &sp, &a_bar, &a_err};
+    CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_fwd_kernel, dim3(H / kUPC), dim3(256), args, seq_fwd_smem(H), st));
+  } else {
+    // k-major copy of W_hh for the recurrent products (the weights change every iteration)
     dim3 tg((H + 31) / 32, (3 * H + 31) / 32), tb(32, 8);
     transpose_kernel<<<tg, tb, 0, st>>>(P + so[SEG_WHH], t->whh_t.p, 3 * H, H);
-  }
-  for (int tt = 0; tt < L; ++tt) {
-    if (nb[tt] == 0) break;
-    const size_t o = (size_t)tt * B;
-    splitk_gemm_kernel<<<dim3((3 * H + 63) / 64, kSplit), 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H,
-                                                                        nb[tt], 3 * H, H, 0, t->skpart.p, t->tickets);
-    gru_gate_fwd_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, P + so[SEG_BHH], t->gi.p + o * 3 * H,
-                                                                  t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
-                                                                  t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, nb[tt], H);
+    for (int tt = 0; tt < L; ++tt) {
+      if (nb[tt] == 0) break;
+      const size_t o = (size_t)tt * B;
+      splitk_gemm_kernel<<<dim3((3 * H + 63) / 64, kSplit), 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H,
+                                                                          nb[tt], 3 * H, H, 0, t->skpart.p, t->tickets);
+      gru_gate_fwd_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, P + so[SEG_BHH], t->gi.p + o * 3 * H,
+                                                                    t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
+                                                                    t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, nb[tt], H);
+    }
   }
   CUT(cudaGetLastError());
   const float* out = t->hs.p + (size_t)B * H;  // out[t] = h_t ; padded rows stay zero
@@ -714,16 +1050,25 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   if (int rc = gemm<true, false>(st, t->sc, t->dz1.p, out, nullptr, nullptr, G + so[SEG_W1], H, H, (int)R)) return rc;
   colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dz1.p, G + so[SEG_B1], (int)R, H);
   if (int rc = gemm<false, false>(st, t->sc, t->dz1.p, P + so[SEG_W1], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
-  for (int tt = L - 1; tt >= 0; --tt) {
-    if (nb[tt] == 0) continue;
-    const size_t o = (size_t)tt * B;
-    gru_bwd_step_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->dout.p + o * H, t->carry.p, t->r.p + o * H,
-                                                                  t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H,
-                                                                  t->hs.p + o * H, t->dgi.p + o * 3 * H,
-                                                                  t->dgh.p + o * 3 * H, nb[tt], H);
-    // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
-    splitk_gemm_kernel<<<dim3((H + 63) / 64, kSplit), 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p,
-                                                                    H, nb[tt], H, 3 * H, 1, t->skpart.p, t->tickets);
+  if (t->seq_mode == 1) {
+    const float* a_whh = P + so[SEG_WHH]; const float* a_dout = t->dout.p; const float* a_r = t->r.p;
+    const float* a_z = t->z.p; const float* a_n = t->n.p; const float* a_hn = t->hn.p; const float* a_hs = t->hs.p;
+    float* a_dgi = t->dgi.p; float* a_dgh = t->dgh.p; float* a_carry = t->carry.p;
+    unsigned* a_bar = t->seq_bar + 1; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
+    void* args[] = {&a_whh, &a_dout, &a_r, &a_z, &a_n, &a_hn, &a_hs, &a_dgi, &a_dgh, &a_carry, &sp, &a_bar, &a_err};
+    CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_bwd_kernel, dim3(H / kUPC), dim3(256), args, seq_bwd_smem(H), st));
+  } else {
+    for (int tt = L - 1; tt >= 0; --tt) {
+      if (nb[tt] == 0) continue;
+      const size_t o = (size_t)tt * B;
+      gru_bwd_step_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->dout.p + o * H, t->carry.p, t->r.p + o * H,
+                                                                    t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H,
+                                                                    t->hs.p + o * H, t->dgi.p + o * 3 * H,
+                                                                    t->dgh.p + o * 3 * H, nb[tt], H);
+      // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
+      splitk_gemm_kernel<<<dim3((H + 63) / 64, kSplit), 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p,
+                                                                      H, nb[tt], H, 3 * H, 1, t->skpart.p, t->tickets);
+    }
   }
   CUT(cudaGetLastError());
   if (int rc = gemm<true, false>(st, t->sc, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
@@ -734,6 +1079,9 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
   if (mode == 2) return 0;  // gradients + statistics stay on the device for uis_trainer_comm_export()
   return finish_step(t, st, mode, losses_out);
 }
+}  // namespace
+
+extern "C" {
 
 // Losses of the last `count` (<= 4096) calls to uis_trainer_step, oldest first: out[count][3] (host).  Synchronises.
 int uis_trainer_losses(uis_trainer* t, int count, float* out) {
@@ -741,6 +1089,11 @@ int uis_trainer_losses(uis_trainer* t, int count, float* out) {
   if (count > t->calls || count > t->hist_cap) return uis::api_fail(UIS_ERR_INVALID, "only %lld steps recorded", t->calls);
   CUT(cudaSetDevice(t->device));
   CUT(cudaDeviceSynchronize());
+  if (t->seq_bar) {
+    int flag = 0;
+    CUT(cudaMemcpy(&flag, t->seq_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return uis::api_fail(UIS_ERR_CUDA, "persistent recurrence kernel: grid barrier timed out");
+  }
   for (int i = 0; i < count; ++i) {
     const long long slot = (t->calls - count + i) % t->hist_cap;
     CUT(cudaMemcpy(out + 3 * i, t->loss_hist.p + 3 * slot, 3 * sizeof(float), cudaMemcpyDeviceToHost));

@@ -58,7 +58,8 @@ EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destr
            'uis_model_constants', 'uis_predict', 'uis_predict_device',
            'uis_predict_workspace_bytes', 'uis_get_stats', 'uis_trainer_create',
            'uis_trainer_destroy', 'uis_trainer_step', 'uis_trainer_get', 'uis_trainer_losses',
-           'uis_trainer_comm_size', 'uis_trainer_comm_export', 'uis_trainer_comm_apply')
+           'uis_trainer_comm_size', 'uis_trainer_comm_export', 'uis_trainer_comm_apply',
+           'uis_trainer_set_corpus', 'uis_trainer_step_corpus')
 
 
 class TrainHParams(C.Structure):
@@ -119,6 +120,10 @@ def load_library():
   lib.uis_trainer_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
   lib.uis_trainer_losses.restype = C.c_int
   lib.uis_trainer_losses.argtypes = [C.c_void_p, C.c_int, fp]
+  lib.uis_trainer_set_corpus.restype = C.c_int
+  lib.uis_trainer_set_corpus.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+  lib.uis_trainer_step_corpus.restype = C.c_int
+  lib.uis_trainer_step_corpus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, fp, C.c_void_p]
   lib.uis_trainer_comm_size.restype = C.c_int64
   lib.uis_trainer_comm_size.argtypes = [C.c_void_p]
   lib.uis_trainer_comm_export.restype = C.c_int
@@ -304,6 +309,28 @@ class NativeTrainer:
     if count:
       _check(self._lib, self._lib.uis_trainer_losses(self._h, count, out.ctypes.data_as(C.POINTER(C.c_float))))
     return out
+
+  def set_corpus(self, rows, index_lists):
+    """rows: float64 [N, D] concatenated training sequence; index_lists: one int array of row indices per
+    sub-sequence (utils.resize_indices).  Everything is copied to the device once."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    assert rows.ndim == 2 and rows.shape[1] == self.D
+    offsets = np.zeros(len(index_lists) + 1, np.int64)
+    np.cumsum([len(ix) for ix in index_lists], out=offsets[1:])
+    flat = (np.concatenate(index_lists) if len(index_lists) else np.zeros(0)).astype(np.int32)
+    _check(self._lib, self._lib.uis_trainer_set_corpus(
+        self._h, rows.ctypes.data_as(C.c_void_p), rows.shape[0], flat.ctypes.data_as(C.c_void_p), len(flat),
+        offsets.ctypes.data_as(C.c_void_p), len(index_lists)))
+
+  def step_corpus(self, chosen, mode=0, want_losses=False, stream=0):
+    """One iteration on sub-sequences `chosen` (ids in column order, lengths descending).  mode as in
+    uis_trainer_step; asynchronous unless want_losses."""
+    ids = np.ascontiguousarray(chosen, dtype=np.int32)
+    losses = np.zeros(3, np.float32) if want_losses else None
+    _check(self._lib, self._lib.uis_trainer_step_corpus(
+        self._h, ids.ctypes.data_as(C.c_void_p), len(ids), mode,
+        losses.ctypes.data_as(C.POINTER(C.c_float)) if want_losses else None, C.c_void_p(stream)))
+    return tuple(float(v) for v in losses) if want_losses else None
 
   def comm_size(self):
     return int(self._lib.uis_trainer_comm_size(self._h))

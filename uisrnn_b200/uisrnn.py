@@ -179,11 +179,13 @@ class UISRNN:
     optimizer = self._get_optimizer(optimizer=args.optimizer, learning_rate=args.learning_rate)
     if self._native_fit_supported(args):
       self._sync_replicas()
+    if self._native_fit_supported(args):
+      # device-resident training set: row indices per sub-sequence instead of num_permutations copies
+      index_lists, seq_lengths = utils.resize_indices(train_cluster_id, args.num_permutations)
+      self._fit_native(train_sequence, index_lists, seq_lengths, args)
+      return
     sub_sequences, seq_lengths = utils.resize_sequence(
         sequence=train_sequence, cluster_id=train_cluster_id, num_permutations=args.num_permutations)
-    if self._native_fit_supported(args):
-      self._fit_native(sub_sequences, seq_lengths, args)
-      return
     batch = None
     if args.batch_size is None:  # "batch learning": one fixed batch holding every sub-sequence
       batch = utils.pack_sequence(sub_sequences, seq_lengths, None, self.observation_dim, self.device)
@@ -246,10 +248,11 @@ class UISRNN:
             args.batch_size is not None and 1 <= args.batch_size <= 32 and
             os.environ.get('UISRNN_B200_TORCH_FIT', '0') != '1')
 
-  def _fit_native(self, sub_sequences, seq_lengths, args):
-    """fit_concatenated's iteration loop (uisrnn.py:252-311) on libuisrnn_b200.so: parameters,
-    gradients and Adam state stay on the device; per iteration only the batch goes up and three
-    loss scalars come back."""
+  def _fit_native(self, train_sequence, index_lists, seq_lengths, args):
+    """fit_concatenated's iteration loop (uisrnn.py:252-311) on libuisrnn_b200.so: the training set,
+    parameters, gradients and Adam state stay on the device; per iteration only the ids of the drawn
+    sub-sequences go up (the batch is gathered on the device) and the loss scalars are read back
+    when they are logged."""
     from . import native
     import torch.distributed as dist
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
@@ -266,20 +269,20 @@ class UISRNN:
     trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
     self.last_training_losses = []
     comm = torch.zeros(trainer.comm_size(), dtype=torch.float32, device=self.device) if world > 1 else None
+    sampler = utils.BatchSampler(seq_lengths, args.batch_size)
     try:
+      trainer.set_corpus(train_sequence, index_lists)
       pending = 0  # steps enqueued since the losses were last read back
       for num_iter in range(args.train_iteration):
-        # the device works on iteration i while the host packs the batch of iteration i + 1
-        rnn_input, lengths = utils.pack_batch(sub_sequences, seq_lengths, args.batch_size, self.observation_dim)
+        chosen, _ = sampler.draw()  # same np.random.choice call as utils.pack_sequence
         if world == 1:
-          trainer.step_async(rnn_input.astype(np.float32), lengths)
+          trainer.step_corpus(chosen)  # asynchronous: the host runs ahead of the device
         else:
           # local forward/backward on this rank's columns -> ONE all-reduce(sum) of [gradients | loss
           # statistics] over NCCL -> identical normalise / clip / Adam step on every rank
-          mine = shard_columns(len(lengths), rank, world)
+          mine = shard_columns(len(chosen), rank, world)
           if len(mine):
-            local_lengths = lengths[mine]
-            trainer.step_shard(rnn_input[:local_lengths[0], mine, :].astype(np.float32), local_lengths)
+            trainer.step_corpus(chosen[mine], mode=2)
             trainer.comm_export(comm.data_ptr())
           else:
             comm.zero_()

@@ -91,6 +91,14 @@ def resize_sequence(sequence, cluster_id, num_permutations=None):
   Returns `(sub_sequences, seq_lengths)`: one array per speaker (times `num_permutations` block
   permutations when > 1), speakers in `np.unique` order, and each length + 1.
   """
+  index_lists, seq_lengths = resize_indices(cluster_id, num_permutations)
+  return [sequence[indices, :] for indices in index_lists], seq_lengths
+
+
+def resize_indices(cluster_id, num_permutations=None):
+  """`resize_sequence` without the data: the ROW INDICES of every sub-sequence (same order, same
+  `np.random.permutation` calls) and each length + 1.  The device-resident training path gathers rows
+  by these indices instead of holding `num_permutations` float64 copies of the training set."""
   cluster_id = np.asarray(cluster_id)
   unique_ids, inverse = np.unique(cluster_id, return_inverse=True)
   order = np.argsort(inverse, kind='stable')          # indices grouped by speaker, ascending inside
@@ -101,12 +109,29 @@ def resize_sequence(sequence, cluster_id, num_permutations=None):
     indices = order[bounds[k]:bounds[k + 1]]
     if permute:
       for sampled in sample_permuted_segments(indices, num_permutations):
-        sub_sequences.append(sequence[sampled, :])
+        sub_sequences.append(sampled)
         seq_lengths.append(len(indices) + 1)
     else:
-      sub_sequences.append(sequence[indices, :])
+      sub_sequences.append(indices)
       seq_lengths.append(len(indices) + 1)
   return sub_sequences, seq_lengths
+
+
+class BatchSampler:
+  """The draw of `pack_sequence` (utils.py:230-237) without building the batch: `draw()` makes the same
+  `np.random.choice(num_clusters, batch_size)` call and returns the ids of the chosen sub-sequences in
+  column order (lengths descending) with their lengths (+ 1 for the zero frame)."""
+
+  def __init__(self, seq_lengths, batch_size):
+    seq_lengths = np.asarray(seq_lengths)
+    self.batch_size = batch_size
+    self.sorted_lengths = np.sort(seq_lengths)[::-1]
+    self.permute_index = np.argsort(seq_lengths)[::-1]
+
+  def draw(self):
+    count = len(self.sorted_lengths)
+    chosen = np.arange(count) if self.batch_size is None else np.sort(np.random.choice(count, self.batch_size))
+    return self.permute_index[chosen], self.sorted_lengths[chosen]
 
 
 def pack_batch(sub_sequences, seq_lengths, batch_size, observation_dim):
