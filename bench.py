@@ -155,7 +155,7 @@ def secondary_metrics(model, torch):
     np.random.seed(0); random.seed(0)
     seqs, ids = synth_training_set(2000, 500, n_frames=100, dim=DIM, n_spk=3)
     xcat, ycat = utils.concatenate_training_data(seqs, ids, True, True)
-    subs, lens = utils.resize_sequence(xcat, np.array(ycat), 10)
+    index_lists, lens = utils.resize_indices(np.array(ycat), 10)
     w = dict(np.load(MODEL_FIXTURE))
     params = {'gru.weight_ih_l0': w['weight_ih_l0'], 'gru.weight_hh_l0': w['weight_hh_l0'], 'gru.bias_ih_l0': w['bias_ih_l0'],
               'gru.bias_hh_l0': w['bias_hh_l0'], 'linear_mean1.weight': w['w1'], 'linear_mean1.bias': w['b1'],
@@ -164,18 +164,20 @@ def secondary_metrics(model, torch):
     hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5,
           'grad_max_norm': 5.0, 'train_sigma2': True}
     tr = native.NativeTrainer(params, hp)
-    iters, rows = 30, 0
-    for i in range(3 + iters):
-      if i == 3:
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-      xi, li = utils.pack_batch(subs, lens, 32, DIM)
-      if i >= 3:
+    tr.set_corpus(xcat, index_lists)             # as UISRNN.fit does: training set resident on the device
+    sampler = utils.BatchSampler(lens, 32)
+    iters, rows = 100, 0
+    for i in range(5 + iters):
+      if i == 5:
+        tr.losses(1); t0 = time.perf_counter()
+      chosen, li = sampler.draw()
+      if i >= 5:
         rows += int(li.sum())
-      tr.step_async(xi.astype(np.float32), li)   # as UISRNN.fit does: host packs batch i+1 while the device runs i
+      tr.step_corpus(chosen)                     # asynchronous; the batch is gathered on the device
     tr.losses(1)                                 # synchronises
     dt = time.perf_counter() - t0
     out['config4_fit_batch32'] = {'ms_per_iteration': 1e3 * dt / iters, 'packed_rows_per_s': rows / dt,
-                                  'includes': 'host batch packing + H2D + forward/backward/clip/Adam kernels'}
+                                  'includes': 'batch draw (host RNG) + device gather + forward/backward/clip/Adam kernels'}
     tr.close()
   except Exception as err:  # pylint: disable=broad-except
     out['config4_fit_batch32'] = {'error': str(err)[:200]}

@@ -31,11 +31,15 @@ for mode in ('native', 'torch'):
     params['sigma2'] = model.sigma2.detach().cpu().numpy()
     hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5, 'grad_max_norm': 5.0, 'train_sigma2': True}
     tr = native.NativeTrainer(params, hp)
+    np.random.seed(1)
+    index_lists, lens_i = utils.resize_indices(np.array(y), t.num_permutations)
+    tr.set_corpus(x, index_lists)
+    sampler = utils.BatchSampler(lens_i, 32)
     t0 = time.perf_counter()
     for _ in range(iters):
-      xi, li = utils.pack_batch(subs, lens, 32, 256)
+      chosen, li = sampler.draw()
       rows += int(li.sum())
-      tr.step_async(xi.astype(np.float32), li)
+      tr.step_corpus(chosen)
     tr.losses(1)
     dt = time.perf_counter() - t0
   else:

@@ -36,7 +36,10 @@ namespace uis {
 constexpr int kStages = 2;              // weight ring depth
 constexpr int kStageBytes = 48 * 1024;  // bytes per ring stage
 constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
-constexpr int kCPBeam = 20;             // GRU columns per weight pass, look_ahead-1 kernel (two lanes need <= 20 in ~99 % of the steps)
+#ifndef UIS_CP_BEAM
+#define UIS_CP_BEAM 20
+#endif
+constexpr int kCPBeam = UIS_CP_BEAM;             // GRU columns per weight pass, look_ahead-1 kernel (two lanes need <= 20 in ~99 % of the steps)
 constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
 constexpr int kMaxLanes = 4;
 constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
@@ -133,7 +136,7 @@ struct Cfg {
 };
 
 struct SmemLayout {
-  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, total;
+  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, phase, total;
   // offsets inside one lane block
   unsigned l_xt, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
 };
@@ -176,6 +179,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   L.cols = o;      o += align_up(6u * G * B * 4, 16);  // collane, colsrc, colnew, colvis, colrow (8 B each)
   L.bars = o;      o += 2 * kStages * 8;
   L.misc = o;      o += 64;
+  L.phase = o;     o += 128;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters
   L.total = o;
   return L;
 }
@@ -607,11 +611,17 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   const ColCtx cc{collane, colsrc, colnew, colvis, colrow};
 
   unsigned it = 0;  // weight-ring tile counter (identical in every consumer thread)
-  unsigned long long st_cols = 0, st_pass = 0, st_cand = 0, st_steps = 0;
-  int st_maxk = 0;
-  // per-phase cycle counters (thread 0 only): select, gather, gru, w1, w2, advance
-  long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tmark = clock64();
+  // Statistics are thread 0's alone and live in shared memory: as locals they would hold ~30 registers in
+  // every thread across the whole kernel.  ph[0..9]: per-phase cycle counters, ph[10]: phase mark,
+  // ph[11..15]: columns, passes, candidates, steps, max K.
+  long long* ph = reinterpret_cast<long long*>(smem + L.phase);
+  if (tid == 0) {
+    for (int i = 0; i < 16; ++i) ph[i] = 0;
+    ph[10] = clock64();
+  }
+  long long& tmark = ph[10];
+  long long& st_cols = ph[11]; long long& st_pass = ph[12]; long long& st_cand = ph[13]; long long& st_steps = ph[14];
+  long long& st_maxk = ph[15];
 #define UIS_PHASE(i)                         \
   do {                                       \
     if (tid == 0) {                          \
@@ -1041,7 +1051,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       fin[g] = act && (failed || ls[LS_NWIN] == 0 || ls[LS_T] + 1 >= ls[LS_TN]);
       if (tid == 0 && act) {
         const int* nK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + (ls[LS_GEN] ^ 1) * 4 * B;
-        for (int r = 0; r < ls[LS_NWIN]; ++r) st_maxk = max(st_maxk, nK[r]);
+        for (int r = 0; r < ls[LS_NWIN]; ++r) st_maxk = max(st_maxk, (long long)nK[r]);
       }
     }
     for (int g = 0; g < G; ++g) {  // debug taps of finishing lanes (all threads)
@@ -1109,10 +1119,10 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   if (tid == 0) {
     __threadfence_block();
     misc[MI_DONE] = 1;
-    atomicAdd(&p.stats[0], st_cols);
-    atomicAdd(&p.stats[1], st_pass);
-    atomicAdd(&p.stats[2], st_cand);
-    atomicAdd(&p.stats[3], st_steps);
+    atomicAdd(&p.stats[0], (unsigned long long)st_cols);
+    atomicAdd(&p.stats[1], (unsigned long long)st_pass);
+    atomicAdd(&p.stats[2], (unsigned long long)st_cand);
+    atomicAdd(&p.stats[3], (unsigned long long)st_steps);
     atomicMax(&p.stats[4], (unsigned long long)st_maxk);
     for (int i = 0; i < 10; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }

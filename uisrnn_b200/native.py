@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libuisrnn_b200.so')
+# UISRNN_B200_LIB: developer switch for A/B runs of differently tuned builds (tools/); default = the in-tree build
+LIB_PATH = os.environ.get('UISRNN_B200_LIB') or os.path.join(_HERE, 'libuisrnn_b200.so')
 
 UIS_OK = 0
 UIS_ERR_INVALID = -1
