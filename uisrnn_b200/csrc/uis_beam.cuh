@@ -207,7 +207,7 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
       const unsigned bytes = seg < ngru ? C::KT_HH * 3 * H * 4 : (seg == ngru ? C::KT_1 * H * 4 : C::KT_2 * D * 4);
       for (int t = 0; t < ntiles; ++t, ++it) {
         const unsigned s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_parked(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], bytes);
         tma_bulk_g2s(reinterpret_cast<char*>(ring) + (size_t)s * kStageBytes,
                      reinterpret_cast<const char*>(src) + (size_t)t * bytes, bytes, &full[s]);
