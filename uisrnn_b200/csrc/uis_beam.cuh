@@ -553,7 +553,6 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   extern __shared__ __align__(128) unsigned char smem[];
   const int B = p.B, Kcap = p.Kcap, G = p.G;
   const SmemLayout L = make_layout<H, D>(B, Kcap, G);
-  float* smem_f = reinterpret_cast<float*>(smem);
   float* ring = reinterpret_cast<float*>(smem + L.ring);
   float* XA = reinterpret_cast<float*>(smem + L.xa);
   float* XB = reinterpret_cast<float*>(smem + L.xb);

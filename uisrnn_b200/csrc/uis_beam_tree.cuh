@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(Cfg<H, D, kCPTree>::BLOCK, 1) uis_beam_tree_ke
   extern __shared__ __align__(128) unsigned char smem[];
   const int B = p.B, Kcap = p.Kcap, L = p.L, NI = p.node_cap, NLF = p.leaf_cap;
   const TreeLayout T = make_tree_layout<H, D>(B, Kcap, L, NI, NLF, p.P);
-  float* smem_f = reinterpret_cast<float*>(smem);
   float* ring = reinterpret_cast<float*>(smem + T.ring);
   float* XA = reinterpret_cast<float*>(smem + T.xa);
   float* XB = reinterpret_cast<float*>(smem + T.xb);

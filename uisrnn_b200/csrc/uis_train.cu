@@ -292,6 +292,17 @@ __global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restric
     reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(whh + (size_t)(g * H + j0 + u) * H)[k4];
   }
   __syncthreads();
+  // gate thread (b, u): biases once; W_ih x + b_ih of the NEXT step is fetched before the barrier it has to sit out
+  const int gb = tid & 31, gu = tid >> 5, gj = j0 + gu;
+  float bh0 = 0.f, bh1 = 0.f, bh2 = 0.f, gi0 = 0.f, gi1 = 0.f, gi2 = 0.f;
+  if (tid < 32 * kUPC) { bh0 = bhh[gj]; bh1 = bhh[H + gj]; bh2 = bhh[2 * H + gj]; }
+  auto fetch_gi = [&](int t) {
+    if (tid < 32 * kUPC && t < sp.L && gb < seq_rows_alive(sp, t)) {
+      const float* gir = gi + ((size_t)t * B + gb) * 3 * H;
+      gi0 = gir[gj]; gi1 = gir[H + gj]; gi2 = gir[2 * H + gj];
+    }
+  };
+  fetch_gi(0);
   for (int t = 0; t < sp.L; ++t) {
     const int nb = seq_rows_alive(sp, t);
     if (nb == 0) break;
@@ -330,17 +341,17 @@ __global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restric
           for (int ww = 0; ww < 8; ++ww) a += sred[(ww * 3 * kUPC + g * kUPC + u) * 32 + b];
           g3[g] = a;
         }
-        const float* gir = gi + (o + b) * 3 * H;
-        const float r = sigmoid_f32(gir[j] + (g3[0] + bhh[j]));
-        const float z = sigmoid_f32(gir[H + j] + (g3[1] + bhh[H + j]));
-        const float hn = g3[2] + bhh[2 * H + j];
-        const float n = tanhf(gir[2 * H + j] + r * hn);
+        const float r = sigmoid_f32(gi0 + (g3[0] + bh0));
+        const float z = sigmoid_f32(gi1 + (g3[1] + bh1));
+        const float hn = g3[2] + bh2;
+        const float n = tanhf(gi2 + r * hn);
         const float hp = sh[b * S + j];
         const size_t q = (o + b) * H + j;
         hs[q + (size_t)B * H] = (hp - n) * z + n;
         r_o[q] = r; z_o[q] = z; n_o[q] = n; hn_o[q] = hn;
       }
     }
+    fetch_gi(t + 1);
     seq_grid_sync(bar, (unsigned)(t + 1) * gridDim.x, err);
   }
 }
@@ -357,45 +368,59 @@ __global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restric
   const int H = sp.H, B = sp.B, H3 = 3 * H, CH = H3 / 4, S = CH + 4, rpw = CH / 8;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, j0 = blockIdx.x * kUPC;
   float4* sWT = seq_smem;                                 // [3H]: W_hh[row][j0 .. j0 + 3]
-  float* sg = reinterpret_cast<float*>(sWT + H3);         // [32][CH + 4]
-  float4* sred = reinterpret_cast<float4*>(sg + 32 * S);  // [8][32]
+  float* sg = reinterpret_cast<float*>(sWT + H3);         // [2][32][CH + 4]
+  float4* sred = reinterpret_cast<float4*>(sg + 2 * 32 * S);  // [8][32]
   float* scarry = reinterpret_cast<float*>(sred + 8 * 32);  // [32][4]
   for (int i = tid; i < H3; i += 256) sWT[i] = *reinterpret_cast<const float4*>(whh + (size_t)i * H + j0);
   if (tid < 32 * kUPC) scarry[tid] = 0.f;
   __syncthreads();
+  // gate thread (b, u): the saved activations of the NEXT step are fetched while this step's product runs
+  const int ab = tid >> 2, au = tid & 3, aj = j0 + au;
+  float a_do = 0.f, a_r = 0.f, a_z = 0.f, a_n = 0.f, a_hn = 0.f, a_hp = 0.f;
+  auto fetch_a = [&](int t) {
+    if (tid < 32 * kUPC && t >= 0 && ab < seq_rows_alive(sp, t)) {
+      const size_t q = ((size_t)t * B + ab) * H + aj;
+      a_do = dout[q]; a_r = r_i[q]; a_z = z_i[q]; a_n = n_i[q]; a_hn = hn_i[q]; a_hp = hs[q];
+    }
+  };
+  fetch_a(sp.L - 1);
   unsigned epoch = 0;
-  for (int t = sp.L - 1; t >= 0; --t) {
+  for (int t = sp.L - 1; t >= 0; --t) {  // lengths[0] == L: every step has at least one live row
     const int nb = seq_rows_alive(sp, t);
-    if (nb == 0) continue;
     const size_t o = (size_t)t * B;
-    if (tid < 32 * kUPC) {
-      const int b = tid >> 2, u = tid & 3, j = j0 + u;
-      if (b < nb) {
-        const size_t q = (o + b) * H + j;
-        const float dh = dout[q] + scarry[tid];
-        const float r = r_i[q], z = z_i[q], n = n_i[q], hn = hn_i[q], hp = hs[q];
-        const float dn = dh * (1.f - z), dz = dh * (hp - n);
-        const float dan = dn * (1.f - n * n);
-        const float dar = dan * hn * r * (1.f - r);
-        const float daz = dz * z * (1.f - z);
-        float* gi = dgi + (o + b) * H3;
-        float* gh = dgh + (o + b) * H3;
-        gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
-        gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = dan * r;
-        scarry[tid] = dh * z;
-      }
+    if (tid < 32 * kUPC && ab < nb) {
+      const float dh = a_do + scarry[tid];
+      const float r = a_r, z = a_z, n = a_n, hn = a_hn, hp = a_hp;
+      const float dn = dh * (1.f - z), dz = dh * (hp - n);
+      const float dan = dn * (1.f - n * n);
+      const float dar = dan * hn * r * (1.f - r);
+      const float daz = dz * z * (1.f - z);
+      float* gi = dgi + (o + ab) * H3;
+      float* gh = dgh + (o + ab) * H3;
+      gi[aj] = dar; gi[H + aj] = daz; gi[2 * H + aj] = dan;
+      gh[aj] = dar; gh[H + aj] = daz; gh[2 * H + aj] = dan * r;
+      scarry[tid] = dh * z;
     }
     seq_grid_sync(bar, ++epoch * gridDim.x, err);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c0 = 0; c0 < H3; c0 += CH) {
-      for (int i = tid; i < nb * (CH / 4); i += 256) {  // dGh_t, written by every CTA before the barrier
+    fetch_a(t - 1);
+    // dGh_t (written by every CTA before the barrier) streams through two staging buffers: L2 -> smem copies
+    // (cp.async.cg: L2 only, never a stale L1 line) of chunk c + 1 run under the product with chunk c
+    auto stage = [&](int c) {
+      float* dst = sg + (c & 1) * 32 * S;
+      for (int i = tid; i < nb * (CH / 4); i += 256) {
         const int b = i / (CH / 4), c4 = i % (CH / 4);
-        *reinterpret_cast<float4*>(sg + b * S + 4 * c4) = __ldcg(reinterpret_cast<const float4*>(dgh + (o + b) * H3 + c0) + c4);
+        cp_async16(dst + b * S + 4 * c4, dgh + (o + b) * H3 + (size_t)c * CH + 4 * c4);
       }
+      cp_async_commit();
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    stage(0);
+    for (int c = 0; c < 4; ++c) {
+      if (c + 1 < 4) { stage(c + 1); cp_async_wait_but_one(); } else { cp_async_wait_all(); }
       __syncthreads();
       if (lane < nb) {
-        const float* gb = sg + lane * S + w * rpw;
-        const float4* wt = sWT + c0 + w * rpw;
+        const float* gb = sg + (c & 1) * 32 * S + lane * S + w * rpw;
+        const float4* wt = sWT + c * CH + w * rpw;
         for (int rr = 0; rr < rpw; rr += 4) {
           const float4 g4 = *reinterpret_cast<const float4*>(gb + rr);
           const float4 w0 = wt[rr], w1 = wt[rr + 1], w2 = wt[rr + 2], w3 = wt[rr + 3];
@@ -405,17 +430,14 @@ __global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restric
           acc.x = fmaf(g4.w, w3.x, acc.x); acc.y = fmaf(g4.w, w3.y, acc.y); acc.z = fmaf(g4.w, w3.z, acc.z); acc.w = fmaf(g4.w, w3.w, acc.w);
         }
       }
-      __syncthreads();
+      __syncthreads();  // the buffer of chunk c is free for chunk c + 2
     }
     sred[w * 32 + lane] = acc;
     __syncthreads();
-    if (tid < 32 * kUPC) {
-      const int b = tid >> 2, u = tid & 3;
-      if (b < nb) {
-        float a = 0.f;
-        for (int ww = 0; ww < 8; ++ww) a += reinterpret_cast<const float*>(sred + ww * 32 + b)[u];
-        scarry[tid] += a;
-      }
+    if (tid < 32 * kUPC && ab < nb) {
+      float a = 0.f;
+      for (int ww = 0; ww < 8; ++ww) a += reinterpret_cast<const float*>(sred + ww * 32 + ab)[au];
+      scarry[tid] += a;
     }
     __syncthreads();
   }
@@ -620,6 +642,7 @@ __global__ void gather_batch_kernel(const float* __restrict__ rows, const int* _
   const float* src = live ? rows + (size_t)index[cols.begin[b] + tt - 1] * D : nullptr;
   for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = live ? src[i] : 0.f;
 }
+__global__ void set_scalar_kernel(float* p, float v) { *p = v; }
 __global__ void cast_rows_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -815,7 +838,7 @@ int uis_trainer_destroy(uis_trainer* t) {
 
 namespace {
 size_t seq_fwd_smem(int H) { return (size_t)(3 * uis::kUPC * H + 32 * (H + 4) + 8 * 3 * uis::kUPC * 32) * 4; }
-size_t seq_bwd_smem(int H) { return (size_t)3 * H * 16 + (size_t)32 * (3 * H / 4 + 4) * 4 + 8 * 32 * 16 + 32 * uis::kUPC * 4; }
+size_t seq_bwd_smem(int H) { return (size_t)3 * H * 16 + (size_t)2 * 32 * (3 * H / 4 + 4) * 4 + 8 * 32 * 16 + 32 * uis::kUPC * 4; }
 
 // Decides once per trainer whether the persistent recurrence kernels can run (H % 128 == 0, the H / 4 CTAs
 // co-resident, cooperative launch supported); UISRNN_B200_TRAIN_STEPWISE=1 forces the per-step launches.
@@ -839,6 +862,15 @@ int seq_setup(uis_trainer* t) {
   CUT(cudaMalloc(&t->seq_bar, 4 * sizeof(unsigned)));
   CUT(cudaMemset(t->seq_bar, 0, 4 * sizeof(unsigned)));
   t->seq_mode = 1;
+  return 0;
+}
+
+// After a synchronisation: did a grid barrier of the persistent recurrence kernels ever time out?
+int seq_check(uis_trainer* t) {
+  if (!t->seq_bar) return 0;
+  int flag = 0;
+  CUT(cudaMemcpy(&flag, t->seq_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return uis::api_fail(UIS_ERR_CUDA, "persistent recurrence kernel: grid barrier timed out");
   return 0;
 }
 
@@ -958,8 +990,7 @@ int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode
   float* G = t->grads.p;
   const int* so = t->seg_off_h;
   float* sum_sq_d = t->small; float* cnt_d = t->small + D; float* nz = t->small + 2 * D;
-  float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 16;
-  (void)p_sumsq; (void)g_sumsq;
+  float* scalars = nz + 1;
   std::vector<int> nb(L);
   for (int tt = 0; tt < L; ++tt) { int c = 0; while (c < B && lengths[c] > tt) ++c; nb[tt] = c; }
 
@@ -1034,8 +1065,7 @@ int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode
   // factor (they are linear in it) and normalised after the all-reduce, in uis_trainer_comm_apply()
   const float* nz_for_bwd = nz;
   if (mode == 2) {
-    const float one = 1.0f;
-    CUT(cudaMemcpyAsync(scalars + 3, &one, sizeof(float), cudaMemcpyHostToDevice, st));
+    set_scalar_kernel<<<1, 1, 0, st>>>(scalars + 3, 1.0f);  // (a pageable H2D copy would synchronise the stream)
     nz_for_bwd = scalars + 3;
   } else {
     loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
@@ -1089,11 +1119,7 @@ int uis_trainer_losses(uis_trainer* t, int count, float* out) {
   if (count > t->calls || count > t->hist_cap) return uis::api_fail(UIS_ERR_INVALID, "only %lld steps recorded", t->calls);
   CUT(cudaSetDevice(t->device));
   CUT(cudaDeviceSynchronize());
-  if (t->seq_bar) {
-    int flag = 0;
-    CUT(cudaMemcpy(&flag, t->seq_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return uis::api_fail(UIS_ERR_CUDA, "persistent recurrence kernel: grid barrier timed out");
-  }
+  if (int rc = seq_check(t)) return rc;
   for (int i = 0; i < count; ++i) {
     const long long slot = (t->calls - count + i) % t->hist_cap;
     CUT(cudaMemcpy(out + 3 * i, t->loss_hist.p + 3 * slot, 3 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1135,6 +1161,7 @@ int uis_trainer_get(uis_trainer* t, int what, float* const* out) {
   if (!t || !out) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   CUT(cudaSetDevice(t->device));
   CUT(cudaDeviceSynchronize());
+  if (int rc = seq_check(t)) return rc;
   const float* src = what == 0 ? t->params.p : t->grads.p;
   for (int s = 0; s < SEG_COUNT; ++s)
     if (out[s])
