@@ -20,6 +20,8 @@ Fixtures written (all float32 where the reference computes in float32):
   model_small.npz    D=64,H=128 model trained by the reference on synthetic data
   model_small_d2.npz, depth2_cases.npz   the same with rnn_depth=2
   small_cases.npz    small-model cases: beam/look_ahead/test_iteration variants, traces
+  ref_checkpoint.uisrnn, ref_checkpoint_cases.npz   a file written by the reference's save() (D=8, H=16)
+                     and the reference's predictions with that model
 Usage:  python oracle/make_golden.py [--only NAME] [--jobs 8]
 """
 import argparse
@@ -329,6 +331,25 @@ def make_depth2_cases(jobs):
   np.savez_compressed(os.path.join(GOLD, 'depth2_cases.npz'), **o)
 
 
+def make_ref_checkpoint():
+  """A checkpoint written by the reference's own save() (uisrnn.py:135-147) + what the reference predicts
+  with that model: pins the file format both ways."""
+  seed_all(11)
+  m, t, i = ref_args(observation_dim=8, rnn_hidden_size=16, train_iteration=400, learning_rate=1e-2,
+                     batch_size=8)
+  seqs, ids = synth.synth_training_set(5400, 30, n_frames=40, dim=8, n_spk=2, noise=0.05)
+  model = ref.UISRNN(m)
+  model.fit(seqs, ids, t)
+  model.save(os.path.join(GOLD, 'ref_checkpoint.uisrnn'))
+  i.beam_size, i.look_ahead, i.test_iteration = 5, 1, 2
+  xs = [synth.synth_utt(5500 + k, n_frames=30, dim=8, n_spk=2, noise=0.05)[0] for k in range(2)]
+  labels = [np.array(model.predict_single(x, i)) for x in xs]
+  np.savez(os.path.join(GOLD, 'ref_checkpoint_cases.npz'), x0=xs[0], x1=xs[1], labels0=labels[0],
+           labels1=labels[1], transition_bias=model.transition_bias,
+           transition_bias_denominator=model.transition_bias_denominator)
+  print('ref checkpoint labels', labels[0][:20], labels[1][:20])
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--only', default=None)
@@ -338,7 +359,7 @@ def main():
   steps = [('model_toy100', make_model_toy100), ('toy_test', lambda: make_toy_test(a.jobs)),
            ('synth500', lambda: make_synth500(a.jobs)), ('model_small', make_model_small),
            ('small_cases', lambda: make_small_cases(a.jobs)), ('model_small_d2', make_model_small_d2),
-           ('depth2_cases', lambda: make_depth2_cases(a.jobs))]
+           ('depth2_cases', lambda: make_depth2_cases(a.jobs)), ('ref_checkpoint', make_ref_checkpoint)]
   for name, fn in steps:
     if a.only and name not in a.only.split(','):
       continue

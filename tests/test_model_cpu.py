@@ -1,6 +1,7 @@
 """UISRNN API on the CPU device: training/prediction plumbing, exceptions, checkpoints, and the
 CPU decoder (uisrnn_b200/beam_cpu.py) against the reference's golden vectors.  CPU only.
 Modelled on the reference's tests/uisrnn_test.py and tests/integration_test.py."""
+import os
 import random
 
 import numpy as np
@@ -164,3 +165,42 @@ def test_module_surface():
   state.append(torch.zeros(1, 1, 2), torch.zeros(1, 1, 3), 0)
   copy = mod.BeamState(state)
   assert copy.trace == [0] and copy.block_counts == [1] and copy.mean_set is not state.mean_set
+
+
+def test_reads_reference_written_checkpoint_and_writes_the_same_format(tmp_path):
+  """tests/golden/ref_checkpoint.uisrnn was written by the reference's own save()
+  (oracle/make_golden.py); load() must reproduce the reference's predictions with it, and save() must
+  write a file of the same structure (keys, types, shapes, dtypes)."""
+  golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+  cases = np.load(os.path.join(golden, 'ref_checkpoint_cases.npz'))
+  m, _, i = uisrnn.parse_arguments([])
+  m.enable_cuda, m.observation_dim, m.rnn_hidden_size, m.verbosity = False, 8, 16, 0
+  model = uisrnn.UISRNN(m)
+  model.load(os.path.join(golden, 'ref_checkpoint.uisrnn'))
+  assert model.transition_bias == float(cases['transition_bias'])
+  assert model.transition_bias_denominator == float(cases['transition_bias_denominator'])
+  i.beam_size, i.look_ahead, i.test_iteration = 5, 1, 2
+  for k in (0, 1):
+    assert model.predict(cases['x%d' % k], i) == cases['labels%d' % k].tolist()
+  ours = str(tmp_path / 'ours.uisrnn')
+  model.save(ours)
+  a = torch.load(os.path.join(golden, 'ref_checkpoint.uisrnn'), weights_only=False)
+  b = torch.load(ours, weights_only=False)
+
+  def signature(v):
+    if isinstance(v, dict):
+      return {k: signature(x) for k, x in v.items()}
+    if isinstance(v, torch.Tensor):
+      return ('tensor', tuple(v.shape), str(v.dtype))
+    if isinstance(v, np.ndarray):
+      return ('ndarray', v.shape, str(v.dtype))
+    return type(v).__name__
+  sig_a, sig_b = signature(a), signature(b)
+  # the reference's own load() casts the denominator to float (uisrnn.py:160-161), so a file saved after a
+  # load holds a float where a file saved right after fit() holds the int count
+  assert sig_a.pop('transition_bias_denominator') == 'int' and sig_b.pop('transition_bias_denominator') == 'float'
+  assert sig_a == sig_b
+  assert list(a) == list(b) and list(a['rnn_state_dict']) == list(b['rnn_state_dict'])   # same key order
+  for k, v in a['rnn_state_dict'].items():
+    assert torch.equal(v, b['rnn_state_dict'][k])
+  assert np.array_equal(a['sigma2'], b['sigma2']) and np.array_equal(a['rnn_init_hidden'], b['rnn_init_hidden'])
