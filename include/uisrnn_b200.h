@@ -51,7 +51,10 @@ typedef struct uis_predict_opts {
   int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
   int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
                              0 = auto (2 when U >= 2 * CTAs, else 1), max 4                    */
-  int32_t reserved[2];
+  int32_t cluster;        /* CTAs per utterance (thread-block cluster, latency mode for few
+                             utterances; default shape, depth 1, look_ahead 1): 0 = auto (4 or 2
+                             when U * cluster <= CTAs), -1 = off, 2 / 4 / 8 = forced               */
+  int32_t reserved;
 } uis_predict_opts;
 
 /* Optional per-call debug / parity taps.  Any pointer may be NULL.  All are HOST buffers
@@ -85,7 +88,7 @@ typedef struct uis_stats {
   float prepass_ms;        /* device time of the input-projection GEMM (CUDA events on `stream`) */
   float beam_ms;           /* device time of the persistent beam-search kernel                 */
   int32_t lanes;           /* lanes per CTA used                                               */
-  int32_t reserved;
+  int32_t cluster;   /* thread-block cluster size the last call used (1 = none) */
   int64_t phase_cycles[10]; /* SM cycles summed over CTAs: [0] re-pack (P4), [1] gather, [2] GRU pass,
                                [3] W1 pass, [4] W2 pass, [5] advance/back-track, [6] frame landing
                                (P0), [7] scoring (P1), [8] ranking (P2), [9] column/slot assignment (P3) */

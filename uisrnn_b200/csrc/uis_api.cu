@@ -134,7 +134,14 @@ bool shape_supported(int H, int D) {
   return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64);
 }
 
-int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t st) {
+int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, int cluster, cudaStream_t st) {
+  if (cluster > 1) {
+    cudaError_t e = cudaSuccess;
+    if (!uis::launch_beam_cluster(H, D, p, ctas, cluster, uis::beam_cluster_smem(H, D, p.B, p.Kcap), st, &e))
+      return fail(UIS_ERR_UNSUPPORTED, "no cluster-mode kernel for hidden=%d dim=%d", H, D);
+    if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "cluster beam kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   const unsigned smem = smem_bytes(H, D, p.B, p.Kcap, p.G);
   if (smem > 227u * 1024u)
     return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d kcap=%d lanes=%d needs %u B of shared memory (> 227 KB); lower kcap",
@@ -181,11 +188,12 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 
 struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
+  int cluster = 1;  // CTAs per utterance (thread-block cluster size); 1 = one CTA per lane group
   int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
   long long rows;
 };
 
-int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o, Plan* pl) {
+int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o, Plan* pl, bool has_taps = false) {
   if (!m || !o || (U > 0 && !off)) return fail(UIS_ERR_INVALID, "null argument");
   if (U < 0) return fail(UIS_ERR_INVALID, "U < 0");
   if (o->beam_size < 1 || o->look_ahead < 1 || o->test_iteration < 1)
@@ -236,6 +244,32 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   }
   pl->G = G;
   pl->ctas = std::max(1, std::min(ctas, std::max((U + G - 1) / G, 1)));
+  // Cluster (latency) mode: with fewer utterances than SMs, a thread-block cluster of 2/4/8 CTAs works on
+  // each utterance (k-split of every weight matrix, uis_beam.cuh).  opts->cluster: 0 = auto (largest of 4, 2
+  // that still gives every utterance its own cluster), -1 = off, 2/4/8 = forced; UISRNN_B200_CLUSTER=0 disables
+  // the automatic choice.
+  pl->cluster = 1;
+  if (!tree && U >= 1 && o->cluster >= 0 && !has_taps && m->depth == 1 && o->lanes <= 1) {
+    int cs = 0;
+    if (o->cluster == 2 || o->cluster == 4 || o->cluster == 8) {
+      cs = o->cluster;
+    } else if (o->cluster == 0) {
+      const char* env = std::getenv("UISRNN_B200_CLUSTER");
+      if (!(env && env[0] == '0'))
+        for (int c : {4, 2})
+          if ((long long)U * c <= ctas) { cs = c; break; }
+    } else {
+      return fail(UIS_ERR_INVALID, "cluster must be -1, 0, 2, 4 or 8");
+    }
+    if (cs > 1 && uis::beam_cluster_smem(m->H, m->D, pl->B, pl->Kcap) <= 227u * 1024u) {
+      const int clusters = std::max(1, std::min(ctas / cs, U));
+      pl->cluster = cs;
+      pl->G = 1;
+      pl->ctas = clusters * cs;
+    } else if (o->cluster > 0) {
+      return fail(UIS_ERR_UNSUPPORTED, "cluster mode needs hidden=512 dim=256 depth=1 and beam_size/kcap that fit in shared memory");
+    }
+  }
   return 0;
 }
 
@@ -256,6 +290,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   m->stats.frames = pl.rows;
   m->stats.ctas = pl.ctas;
   m->stats.lanes = pl.G;
+  m->stats.cluster = pl.cluster;
   m->last_U = U;
   m->last_stream = st;
   m->stats_pending = false;
@@ -357,7 +392,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   }
   CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
-  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st) : dispatch_beam(H, D, p, pl.ctas, st))) return rc;
+  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st) : dispatch_beam(H, D, p, pl.ctas, pl.cluster, st))) return rc;
   CU(cudaEventRecord(m->ev[2], st));
   m->stats.kernel_launches = 2;
   m->stats_pending = true;
@@ -547,7 +582,7 @@ size_t uis_predict_workspace_bytes(uis_model* m, const int64_t* frame_offsets, i
 int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_offsets, int U,
                        const uis_predict_opts* opts, int32_t* labels_dev, const uis_debug_taps* taps, void* stream) {
   Plan pl;
-  if (int rc = make_plan(m, frame_offsets, U, opts, &pl)) return rc;
+  if (int rc = make_plan(m, frame_offsets, U, opts, &pl, taps != nullptr)) return rc;
   if (U > 0 && pl.rows > 0 && (!x_dev || !labels_dev)) return fail(UIS_ERR_INVALID, "null device buffer");
   CU(cudaSetDevice(m->device));
   return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, static_cast<cudaStream_t>(stream));
@@ -564,7 +599,7 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
     off[u + 1] = off[u] + n_frames[u];
   }
   Plan pl;
-  if (int rc = make_plan(m, off.data(), U, opts, &pl)) return rc;
+  if (int rc = make_plan(m, off.data(), U, opts, &pl, taps != nullptr)) return rc;
   CU(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = m->D;

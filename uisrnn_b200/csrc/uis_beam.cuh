@@ -40,6 +40,8 @@ constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
 #define UIS_CP_BEAM 20
 #endif
 constexpr int kCPBeam = UIS_CP_BEAM;             // GRU columns per weight pass, look_ahead-1 kernel (two lanes need <= 20 in ~99 % of the steps)
+constexpr int kCPCluster = 12;          // cluster (latency) mode: one lane per cluster, <= 12 columns per pass
+constexpr int kXchVals = 24;            // floats per thread and exchange round of the cluster K-split
 constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
 constexpr int kMaxLanes = 4;
 constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
@@ -136,7 +138,7 @@ struct Cfg {
 };
 
 struct SmemLayout {
-  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, phase, total;
+  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, phase, xch, xbar, total;
   // offsets inside one lane block
   unsigned l_xt, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
 };
@@ -148,11 +150,10 @@ enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRAC
        LS_NWIN, LS_ERR, LS_M, LS_COLBASE, LS_NE, LS_ROW0_LO, LS_ROW0_HI, LS_DBGROWS_LO, LS_DBGROWS_HI,
        LS_FRESH, LS_COUNT = 24 };
 // CTA scalars
-enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT };
+enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT };
 
-template <int H, int D>
+template <int H, int D, int kCP = kCPBeam, bool XCL = false>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
-  constexpr int kCP = kCPBeam;
   SmemLayout L;
   unsigned o = 0;
   L.ring = o;  o += kStages * kStageBytes;
@@ -180,15 +181,24 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   L.bars = o;      o += 2 * kStages * 8;
   L.misc = o;      o += 64;
   L.phase = o;     o += 128;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters
+  L.xch = o; L.xbar = o;
+  if (XCL) {  // cluster K-split: two exchange buffers of kXchVals floats per consumer thread + 2 mbarriers
+    o = align_up(o, 16);
+    L.xch = o;   o += 2u * kXchVals * (H / ((H >= 512) ? 2 : 1)) * 4;
+    L.xbar = o;  o += 16;
+  }
   L.total = o;
   return L;
 }
 
 // ------------------------------------------------------------------ producer (one thread)
-template <class C>
+template <class C, bool XCL = false>
 __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, uint64_t* empty,
                               volatile int* misc) {
   constexpr int H = C::H, D = C::D;
+  // cluster mode: CTA `rank` of the cluster streams (and multiplies) only its share of the k-tiles of every
+  // matrix -- the k-major layouts split contiguously
+  const int xrank = XCL ? (int)cluster_ctarank() : 0, xsize = XCL ? (int)cluster_nctarank() : 1;
   unsigned it = 0;
   int pass = 0;
   for (;;) {
@@ -205,7 +215,8 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
       else src = (seg == ngru) ? p.w1_t : p.w2_t;
       const int ntiles = seg < ngru ? C::N_HH : (seg == ngru ? C::N_1 : C::N_2);
       const unsigned bytes = seg < ngru ? C::KT_HH * 3 * H * 4 : (seg == ngru ? C::KT_1 * H * 4 : C::KT_2 * D * 4);
-      for (int t = 0; t < ntiles; ++t, ++it) {
+      const int tcnt = ntiles / xsize, tbeg = xrank * tcnt;
+      for (int t = tbeg; t < tbeg + tcnt; ++t, ++it) {
         const unsigned s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait_parked(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], bytes);
@@ -220,8 +231,9 @@ __device__ void producer_loop(const BeamParams& p, float* ring, uint64_t* full, 
 // Consume one full weight pass without computing (a step with no winner at all), so that the
 // producer, which was already told about the pass, never blocks on a full ring.
 template <class C>
-__device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsigned& it, int lane, int depth = 1) {
-  const int tiles = C::TILES_PER_PASS + 2 * (depth - 1) * C::N_HH;
+__device__ __forceinline__ void drain_pass(uint64_t* full, uint64_t* empty, unsigned& it, int lane, int depth = 1,
+                                           int xsize = 1) {
+  const int tiles = (C::TILES_PER_PASS + 2 * (depth - 1) * C::N_HH) / xsize;
   for (int t = 0; t < tiles; ++t, ++it) {
     const unsigned s = it % kStages, ph = (it / kStages) & 1;
     mbar_wait(&full[s], ph);
@@ -242,13 +254,16 @@ struct Operands {
   float4 x[NC];
 };
 
-template <class C, int ROWS, int KT, int KG, int R, int NC, bool ZERO = true>
+template <class C, int ROWS, int KT, int KG, int R, int NC, bool ZERO = true, bool XCL = false>
 __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_t* full, uint64_t* empty,
                                          unsigned& it, const float* __restrict__ X, float (&acc)[R][4 * NC],
-                                         int tid, int lane) {
+                                         int tid, int lane, int xrank = 0, int xsize = 1) {
   constexpr int TG = C::NT / KG;
   constexpr int KPG = KT / KG;
-  constexpr int NTILES = C::H / KT;
+  constexpr int NTILES_ALL = C::H / KT;
+  // cluster mode: this CTA multiplies tiles [TILE0, TILE0 + NTILES) only (a partial sum over k)
+  const int NTILES = XCL ? NTILES_ALL / xsize : NTILES_ALL;
+  const int TILE0 = XCL ? xrank * NTILES : 0;
   const int kg = tid / TG, tl = tid % TG;
   if constexpr (ZERO) {
 #pragma unroll
@@ -299,7 +314,7 @@ __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_
   Operands<R, NC> cur, nxt;
   mbar_wait(&full[it % kStages], (it / kStages) & 1);
   const float* wt = tile_w(it);
-  const float4* xp = tile_x(0);
+  const float4* xp = tile_x(TILE0);
   load(cur, wt, xp, 0);
   for (int tile = 0; tile < NTILES; ++tile) {
     const unsigned s = it % kStages;
@@ -311,7 +326,7 @@ __device__ __forceinline__ void lin_pass(const float* __restrict__ ring, uint64_
         const unsigned itn = it + 1;
         mbar_wait(&full[itn % kStages], (itn / kStages) & 1);
         wt = tile_w(itn);
-        xp = tile_x(tile + 1);
+        xp = tile_x(TILE0 + tile + 1);
         load(nxt, wt, xp, 0);
       }
       mac(cur);
@@ -366,6 +381,62 @@ __device__ __forceinline__ void ksplit_reduce(float (&acc)[R][4 * NC], float* __
   }
 }
 
+// Cluster K-split: all-reduce of NV floats per consumer thread across the CTAs of the cluster, through
+// distributed shared memory.  Every CTA parks its partial values in its own buffer (double-buffered by the
+// exchange count), tells every peer "ready" with a release-arrive on the PEER's mbarrier, waits until all
+// peers have told it the same, and sums the partials of ranks 0, 1, ... in that order -- the same order in
+// every CTA, so the replicas stay bit-identical.  A buffer is rewritten two exchanges later, after the next
+// handshake, by which time every peer has consumed it (in-order issue: the adds below wait for the loads).
+struct XchCtx {
+  float* buf;      // [2][kXchVals][NT]
+  uint64_t* bar;   // [2]
+  unsigned rank, size, count;  // count = exchanges done so far (identical in every thread of the cluster)
+};
+template <int NT, int NV>
+__device__ __forceinline__ void xch_allreduce(XchCtx& x, float (&v)[NV], int tid) {
+  static_assert(NV <= kXchVals, "exchange round too large");
+  const unsigned b = x.count & 1u, parity = (x.count >> 1) & 1u;
+  float* mine = x.buf + (size_t)b * kXchVals * NT;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) mine[i * NT + tid] = v[i];
+  named_bar_sync(1, NT);
+  if (tid == 0)
+    for (unsigned r = 0; r < x.size; ++r)
+      if (r != x.rank) mbar_arrive_remote(dsmem_addr(smem_u32(&x.bar[b]), r));
+  mbar_wait_cluster(&x.bar[b], parity);
+  const uint32_t base = smem_u32(mine + tid);
+  float sum[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sum[i] = 0.f;
+  for (unsigned r = 0; r < x.size; ++r) {
+    if (r == x.rank) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum[i] = (r == 0) ? v[i] : __fadd_rn(sum[i], v[i]);
+    } else {
+      const uint32_t ra = dsmem_addr(base, r);
+      float t[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) t[i] = dsmem_ld_f32(ra + (uint32_t)(i * NT) * 4u);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum[i] = (r == 0) ? t[i] : __fadd_rn(sum[i], t[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sum[i];
+  x.count += 1;
+}
+// handshake without data: nobody leaves (and frees its shared memory) while a peer may still read it
+template <int NT>
+__device__ __forceinline__ void xch_barrier(XchCtx& x, int tid) {
+  const unsigned b = x.count & 1u, parity = (x.count >> 1) & 1u;
+  named_bar_sync(1, NT);
+  if (tid == 0)
+    for (unsigned r = 0; r < x.size; ++r)
+      if (r != x.rank) mbar_arrive_remote(dsmem_addr(smem_u32(&x.bar[b]), r));
+  mbar_wait_cluster(&x.bar[b], parity);
+  x.count += 1;
+}
+
 // Per-column context of the current weight pass (shared memory, written in phase P4).
 struct ColCtx {
   const int* lane;  // [Mtot] lane of the column
@@ -376,19 +447,37 @@ struct ColCtx {
 };
 
 // ---- one full weight pass (GRU -> W1 -> W2) for columns [m0, m0 + Mp) -----------------------
-template <class C, int NC, bool DEEP>
+template <class C, int NC, bool DEEP, bool XCL = false>
 __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
                                          unsigned& it, float* XA, float* XB,
                                          const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
                                          float* pool_hidden_cta, const float (&bh)[C::RG], const float (&b1r)[C::UPT],
-                                         float b2r, int tid, int lane, long long* ph, long long& tmark) {
+                                         float b2r, int tid, int lane, long long* ph, long long& tmark,
+                                         XchCtx* xc = nullptr) {
+  const int xrank = XCL ? (int)xc->rank : 0, xsize = XCL ? (int)xc->size : 1;
   constexpr int H = C::H, D = C::D, NT = C::NT, UPT = C::UPT;
   const int DH = p.depth * H;
   const size_t lane_pool_h = (size_t)p.P * DH, lane_pool_m = (size_t)p.P * D;
   // ---------------- GRU gates: acc[g*UPT + u][m] = (W_h{r,z,n} h_src)[unit tid + NT*u]
   {
     float acc[C::RG][4 * NC];
-    lin_pass<C, 3 * H, C::KT_HH, 1, C::RG, NC>(ring, full, empty, it, XA, acc, tid, lane);
+    lin_pass<C, 3 * H, C::KT_HH, 1, C::RG, NC, true, XCL>(ring, full, empty, it, XA, acc, tid, lane, xrank, xsize);
+    if constexpr (XCL) {  // partial sums over this CTA's k-tiles -> full sums, one 4-column group per round
+      static_assert(!DEEP && 4 * C::RG <= kXchVals, "cluster mode: depth 1");
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float v[4 * C::RG];
+#pragma unroll
+        for (int i = 0; i < C::RG; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[4 * i + q] = acc[i][4 * c + q];
+        xch_allreduce<NT, 4 * C::RG>(*xc, v, tid);
+#pragma unroll
+        for (int i = 0; i < C::RG; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][4 * c + q] = v[4 * i + q];
+      }
+    }
     // GRU cell, PyTorch gate order r,z,n (uisrnn.py:39-47):  h' = (h - n) * z + n
 #pragma unroll
     for (int u = 0; u < UPT; ++u) {
@@ -484,9 +573,22 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
   // ---------------- a = relu(W1 h' + b1)
   {
     float acc[C::R1][4 * NC];
-    lin_pass<C, H, C::KT_1, C::KG1, C::R1, NC>(ring, full, empty, it, XB, acc, tid, lane);
+    lin_pass<C, H, C::KT_1, C::KG1, C::R1, NC, true, XCL>(ring, full, empty, it, XB, acc, tid, lane, xrank, xsize);
     float out[UPT][4 * NC];
     ksplit_reduce<C, H, C::KG1, C::R1, UPT, NC>(acc, XA, out, tid);
+    if constexpr (XCL) {
+      static_assert(UPT * 4 * NC <= kXchVals, "cluster mode: W1 exchange in one round");
+      float v[UPT * 4 * NC];
+#pragma unroll
+      for (int u = 0; u < UPT; ++u)
+#pragma unroll
+        for (int m = 0; m < 4 * NC; ++m) v[u * 4 * NC + m] = out[u][m];
+      xch_allreduce<NT, UPT * 4 * NC>(*xc, v, tid);
+#pragma unroll
+      for (int u = 0; u < UPT; ++u)
+#pragma unroll
+        for (int m = 0; m < 4 * NC; ++m) out[u][m] = v[u * 4 * NC + m];
+    }
 #pragma unroll
     for (int u = 0; u < UPT; ++u)
 #pragma unroll
@@ -509,9 +611,10 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
                       ? pool_mean_cta[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.src[m0 + m] * D + tid]
                       : 0.f;
     float acc[C::R2][4 * NC];
-    lin_pass<C, D, C::KT_2, C::KG2, C::R2, NC>(ring, full, empty, it, XA, acc, tid, lane);
+    lin_pass<C, D, C::KT_2, C::KG2, C::R2, NC, true, XCL>(ring, full, empty, it, XA, acc, tid, lane, xrank, xsize);
     float out[1][4 * NC];
     ksplit_reduce<C, D, C::KG2, C::R2, 1, NC>(acc, XA, out, tid);
+    if constexpr (XCL) xch_allreduce<NT, 4 * NC>(*xc, out[0], tid);
     if (tid < D) {
 #pragma unroll
       for (int m = 0; m < 4 * NC; ++m) {
@@ -530,29 +633,32 @@ __device__ __forceinline__ void run_pass(const BeamParams& p, const float* ring,
 
 // Picks the instantiation by NC = number of 4-column chunks in this pass.  DEEP (stacked GRU layers) is a
 // template parameter of the kernels so that the depth-1 kernels carry none of that code or its registers.
-template <class C, bool DEEP>
+template <class C, bool DEEP, bool XCL = false>
 __device__ __forceinline__ void run_pass_any(const BeamParams& p, const float* ring, uint64_t* full, uint64_t* empty,
                                              unsigned& it, float* XA, float* XB, const ColCtx cc, int m0, int Mp,
                                              float* pool_mean_cta, float* pool_hidden_cta, const float (&bh)[C::RG],
                                              const float (&b1r)[C::UPT], float b2r, int tid, int lane, long long* ph,
-                                             long long& tmark) {
+                                             long long& tmark, XchCtx* xc = nullptr) {
   const int nc = (Mp + 3) / 4;
 #define UIS_RP(NCV, DEEPV) \
-  run_pass<C, NCV, DEEPV>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark)
-  if (nc == 1) UIS_RP(1, DEEP); else if (nc == 2) UIS_RP(2, DEEP); else if (nc == 3) UIS_RP(3, DEEP);
-  else if (nc == 4 || C::CP < 20) UIS_RP(4, DEEP);
+  run_pass<C, NCV, DEEPV, XCL>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark, xc)
+  if (nc == 1) UIS_RP(1, DEEP); else if (nc == 2) UIS_RP(2, DEEP); else if (nc == 3 || C::CP < 16) UIS_RP(3, DEEP);
+  else if (nc == 4 || C::CP < 20) { if constexpr (C::CP >= 16) UIS_RP(4, DEEP); }
   else { if constexpr (C::CP >= 20) UIS_RP(5, DEEP); }
 #undef UIS_RP
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int H, int D, bool DEEP>
+// XCL = cluster (latency) mode: the kernel is launched with thread-block clusters of 2/4/8 CTAs; the CTAs of a
+// cluster run the SAME utterances in lock step (all selection phases replicated, bit-identical), and split every
+// weight matrix by k-tiles, exchanging partial sums through distributed shared memory (xch_allreduce).
+template <int H, int D, bool DEEP, bool XCL = false>
 __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const BeamParams p) {
-  using C = Cfg<H, D>;
+  using C = Cfg<H, D, XCL ? kCPCluster : kCPBeam>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int B = p.B, Kcap = p.Kcap, G = p.G;
-  const SmemLayout L = make_layout<H, D>(B, Kcap, G);
+  const SmemLayout L = make_layout<H, D, C::CP, XCL>(B, Kcap, G);
   float* ring = reinterpret_cast<float*>(smem + L.ring);
   float* XA = reinterpret_cast<float*>(smem + L.xa);
   float* XB = reinterpret_cast<float*>(smem + L.xb);
@@ -570,13 +676,20 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       mbar_init(&empty[s], NW);
     }
     for (int i = 0; i < 16; ++i) misc[i] = 0;
+    if constexpr (XCL) {
+      uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.xbar);
+      mbar_init(&xbar[0], cluster_nctarank() - 1);
+      mbar_init(&xbar[1], cluster_nctarank() - 1);
+      misc[MI_QNEXT] = (int)cluster_id_x();  // utterances are dealt to the clusters round-robin (no atomic queue)
+    }
     fence_mbar_init();
   }
   __syncthreads();
+  if constexpr (XCL) cluster_sync_all();  // every peer's exchange barriers exist before anyone arrives on them
 
   if (warp >= NW) {  // ---------------- producer warp (+ idle warps of its warpgroup)
     if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == NW && lane == 0) producer_loop<C>(p, ring, full, empty, misc);
+    if (warp == NW && lane == 0) producer_loop<C, XCL>(p, ring, full, empty, misc);
     return;
   }
   if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
@@ -608,6 +721,9 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   int* colvis = colarr + 3 * G * B;
   long long* colrow = reinterpret_cast<long long*>(colarr + 4 * G * B);
   const ColCtx cc{collane, colsrc, colnew, colvis, colrow};
+  XchCtx xc{reinterpret_cast<float*>(smem + L.xch), reinterpret_cast<uint64_t*>(smem + L.xbar),
+            XCL ? cluster_ctarank() : 0u, XCL ? cluster_nctarank() : 1u, 0u};
+  const int xsize = (int)xc.size;
 
   unsigned it = 0;  // weight-ring tile counter (identical in every consumer thread)
   // Statistics are thread 0's alone and live in shared memory: as locals they would hold ~30 registers in
@@ -634,7 +750,13 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   auto lane_fetch = [&](int g) {
     volatile int* ls = LSp(g);
     for (;;) {
-      const int uidx = atomicAdd(p.queue, 1);
+      int uidx;
+      if constexpr (XCL) {  // one lane per cluster; every CTA of the cluster draws the same sequence
+        uidx = misc[MI_QNEXT];
+        misc[MI_QNEXT] = uidx + (int)cluster_nclusters_x();
+      } else {
+        uidx = atomicAdd(p.queue, 1);
+      }
       if (uidx >= p.U) { ls[LS_ACTIVE] = 0; ls[LS_FRESH] = 0; return; }
       const int u = p.order[uidx];
       const long long row0 = p.row_off[u];
@@ -1013,7 +1135,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
 
     UIS_PHASE(0);
     // ---- P5: GRU + MLP for the Mtot distinct source states, C::CP columns per weight pass
-    if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth);
+    if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
     for (int m0 = 0; m0 < Mtot; m0 += C::CP) {
       const int Mp = min(C::CP, Mtot - m0);
       // gather the source hidden states, transposed: XA[k][m]
@@ -1035,8 +1157,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       }
       named_bar_sync(1, NT);
       UIS_PHASE(1);
-      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth);
-      else run_pass_any<C, DEEP>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark);
+      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
+      else run_pass_any<C, DEEP, XCL>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark, &xc);
       named_bar_sync(1, NT);
       UIS_PHASE(4);
     }
@@ -1115,9 +1237,11 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
   }  // CTA steps
 
   cp_async_wait_all();
+  if constexpr (XCL) xch_barrier<NT>(xc, tid);  // peers may still be reading this CTA's exchange buffer
   if (tid == 0) {
     __threadfence_block();
     misc[MI_DONE] = 1;
+    if (XCL && xc.rank != 0) return;  // the replicas of a cluster count once
     atomicAdd(&p.stats[0], (unsigned long long)st_cols);
     atomicAdd(&p.stats[1], (unsigned long long)st_pass);
     atomicAdd(&p.stats[2], (unsigned long long)st_cand);

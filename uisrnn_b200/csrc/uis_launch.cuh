@@ -8,6 +8,10 @@ namespace uis {
 // each returns false if (H, D) is not one of its shapes; *err receives the CUDA status otherwise
 bool launch_beam_large(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
 bool launch_beam_small(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+// cluster (latency) mode: `ctas` = clusters * cluster; false if the shape has no cluster instantiation
+bool launch_beam_cluster(int H, int D, const BeamParams& p, int ctas, int cluster, unsigned smem, cudaStream_t st,
+                         cudaError_t* err);
+unsigned beam_cluster_smem(int H, int D, int B, int Kcap);
 bool launch_tree_large(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
 bool launch_tree_small(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
 
