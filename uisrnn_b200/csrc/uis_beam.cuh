@@ -394,11 +394,11 @@ struct XchCtx {
 };
 template <int NT, int NV>
 __device__ __forceinline__ void xch_allreduce(XchCtx& x, float (&v)[NV], int tid) {
-  static_assert(NV <= kXchVals, "exchange round too large");
+  static_assert(NV <= kXchVals && NV % 4 == 0, "exchange round: a multiple of 4, at most kXchVals floats");
   const unsigned b = x.count & 1u, parity = (x.count >> 1) & 1u;
-  float* mine = x.buf + (size_t)b * kXchVals * NT;
+  float4* mine = reinterpret_cast<float4*>(x.buf + (size_t)b * kXchVals * NT);  // [NV / 4][NT] float4
 #pragma unroll
-  for (int i = 0; i < NV; ++i) mine[i * NT + tid] = v[i];
+  for (int i = 0; i < NV / 4; ++i) mine[i * NT + tid] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   named_bar_sync(1, NT);
   if (tid == 0)
     for (unsigned r = 0; r < x.size; ++r)
@@ -414,11 +414,16 @@ __device__ __forceinline__ void xch_allreduce(XchCtx& x, float (&v)[NV], int tid
       for (int i = 0; i < NV; ++i) sum[i] = (r == 0) ? v[i] : __fadd_rn(sum[i], v[i]);
     } else {
       const uint32_t ra = dsmem_addr(base, r);
-      float t[NV];
+      float4 t[NV / 4];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) t[i] = dsmem_ld_f32(ra + (uint32_t)(i * NT) * 4u);
+      for (int i = 0; i < NV / 4; ++i) t[i] = dsmem_ld_f32x4(ra + (uint32_t)(i * NT) * 16u);  // 16 B per thread and load
 #pragma unroll
-      for (int i = 0; i < NV; ++i) sum[i] = (r == 0) ? t[i] : __fadd_rn(sum[i], t[i]);
+      for (int i = 0; i < NV / 4; ++i) {
+        sum[4 * i + 0] = (r == 0) ? t[i].x : __fadd_rn(sum[4 * i + 0], t[i].x);
+        sum[4 * i + 1] = (r == 0) ? t[i].y : __fadd_rn(sum[4 * i + 1], t[i].y);
+        sum[4 * i + 2] = (r == 0) ? t[i].z : __fadd_rn(sum[4 * i + 2], t[i].z);
+        sum[4 * i + 3] = (r == 0) ? t[i].w : __fadd_rn(sum[4 * i + 3], t[i].w);
+      }
     }
   }
 #pragma unroll
