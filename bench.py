@@ -145,7 +145,8 @@ def secondary_metrics(model, torch):
         model.predict_device(xs.data_ptr(), offs, lab.data_ptr(), beam_size=BEAM, look_ahead=LOOK_AHEAD, test_iteration=TEST_ITER)
         stu = model.stats()
       out['config2_U%d' % U1] = {'frames_per_s': U1 * N_FRAMES / ((stu['beam_ms'] + stu['prepass_ms']) / 1e3),
-                                 'ms': stu['beam_ms'] + stu['prepass_ms'], 'ctas': stu['ctas'], 'lanes': stu['lanes']}
+                                 'ms': stu['beam_ms'] + stu['prepass_ms'], 'ctas': stu['ctas'], 'lanes': stu['lanes'],
+                                 'cluster': stu['cluster']}   # CTAs per utterance (latency mode)
   except Exception as err:  # pylint: disable=broad-except
     out['config2_small_batches'] = {'error': str(err)[:200]}
   try:  # config 4: fit() iteration on 50k concatenated frames, batch_size=32 (device trainer, csrc/uis_train.cu)
