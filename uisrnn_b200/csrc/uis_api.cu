@@ -134,13 +134,20 @@ bool shape_supported(int H, int D) {
   return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64);
 }
 
-int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, int cluster, cudaStream_t st) {
-  if (cluster > 1) {
+// *cluster: in = planned cluster size, out = the one that was launched.  When the cluster size was chosen
+// automatically and the cluster launch is refused (e.g. a partitioned GPU that cannot co-schedule the CTAs), the
+// one-CTA-per-utterance kernel runs on the same grid instead: its extra CTAs find the utterance queue empty.
+int dispatch_beam(int H, int D, const uis::BeamParams& p, int ctas, int* cluster, bool cluster_forced, cudaStream_t st) {
+  if (*cluster > 1) {
     cudaError_t e = cudaSuccess;
-    if (!uis::launch_beam_cluster(H, D, p, ctas, cluster, uis::beam_cluster_smem(H, D, p.B, p.Kcap), st, &e))
-      return fail(UIS_ERR_UNSUPPORTED, "no cluster-mode kernel for hidden=%d dim=%d", H, D);
-    if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "cluster beam kernel launch failed: %s", cudaGetErrorString(e));
-    return 0;
+    const bool have = uis::launch_beam_cluster(H, D, p, ctas, *cluster, uis::beam_cluster_smem(H, D, p.B, p.Kcap), st, &e);
+    if (have && e == cudaSuccess) return 0;
+    if (cluster_forced) {
+      if (!have) return fail(UIS_ERR_UNSUPPORTED, "no cluster-mode kernel for hidden=%d dim=%d", H, D);
+      return fail(UIS_ERR_CUDA, "cluster beam kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    (void)cudaGetLastError();  // clear the launch error and fall back
+    *cluster = 1;
   }
   const unsigned smem = smem_bytes(H, D, p.B, p.Kcap, p.G);
   if (smem > 227u * 1024u)
@@ -189,6 +196,7 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
   int cluster = 1;  // CTAs per utterance (thread-block cluster size); 1 = one CTA per lane group
+  bool cluster_forced = false;
   int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
   long long rows;
 };
@@ -264,6 +272,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
     if (cs > 1 && uis::beam_cluster_smem(m->H, m->D, pl->B, pl->Kcap) <= 227u * 1024u) {
       const int clusters = std::max(1, std::min(ctas / cs, U));
       pl->cluster = cs;
+      pl->cluster_forced = o->cluster > 0;
       pl->G = 1;
       pl->ctas = clusters * cs;
     } else if (o->cluster > 0) {
@@ -392,7 +401,11 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   }
   CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
-  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st) : dispatch_beam(H, D, p, pl.ctas, pl.cluster, st))) return rc;
+  int cluster_used = pl.cluster;
+  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st)
+                         : dispatch_beam(H, D, p, pl.ctas, &cluster_used, pl.cluster_forced, st)))
+    return rc;
+  m->stats.cluster = cluster_used;
   CU(cudaEventRecord(m->ev[2], st));
   m->stats.kernel_launches = 2;
   m->stats_pending = true;
