@@ -422,7 +422,7 @@ def run_b200(args):
   }
   if world == 1 and not args.no_secondary:
     out['secondary'] = secondary_metrics(model, torch)
-  if not args.no_cpu_baseline:
+  if world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (a bounded CPU sample, ~35 s)
     out['cpu_baseline'] = cpu_baseline_port()
   print(json.dumps(out), flush=True)
   if world > 1:
