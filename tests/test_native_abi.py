@@ -58,3 +58,6 @@ def test_sass_uses_tma_and_packed_fma():
   from uisrnn_b200 import native
   sass = subprocess.run([tool, '-sass', native.LIB_PATH], capture_output=True, text=True).stdout
   assert 'UBLKCP' in sass and 'SYNCS' in sass and 'FFMA2' in sass
+  # register re-balancing of the warp-specialised CTA, and the cluster (latency) mode: cluster barrier at start-up,
+  # remote mbarrier arrives (the .RED form) for the distributed-shared-memory exchange
+  assert 'USETMAXREG' in sass and 'UCGABAR_ARV' in sass and 'SYNCS.ARRIVE.TRANS64.RED' in sass
