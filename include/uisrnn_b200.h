@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UIS_ABI_VERSION 1
+#define UIS_ABI_VERSION 2
 
 typedef enum uis_status {
   UIS_OK = 0,

@@ -22,6 +22,10 @@ Fixtures written (all float32 where the reference computes in float32):
   small_cases.npz    small-model cases: beam/look_ahead/test_iteration variants, traces
   ref_checkpoint.uisrnn, ref_checkpoint_cases.npz   a file written by the reference's save() (D=8, H=16)
                      and the reference's predictions with that model
+  synth500_bench.npz reference labels of ten utterances of bench.py's workload (seeds 100000 + {0..5, 147, 148, 294, 295})
+  small500.npz       reference labels of four 500-frame utterances with the D=64/H=128 model
+  fit_traj.npz       the reference's fit(): three loss terms of 20 iterations + initial / final parameters
+                     (depth 1 batch 16, depth 1 batch 48, depth 2 without dropout)
 Usage:  python oracle/make_golden.py [--only NAME] [--jobs 8]
 """
 import argparse
@@ -350,6 +354,93 @@ def make_ref_checkpoint():
   print('ref checkpoint labels', labels[0][:20], labels[1][:20])
 
 
+def make_synth500_bench(jobs):
+  """Reference labels for the first utterances of bench.py's own workload (seeds 100000 + u, config 2 shape):
+  pins the kernel variant the bench times (2 lanes, one CTA per lane group) at the full 1000 beam steps."""
+  d = dict(np.load(os.path.join(GOLD, 'model_toy100.npz')))
+  seeds = [100000 + u for u in (0, 1, 2, 3, 4, 5, 147, 148, 294, 295)]  # first / median / last of bench.py's 296
+  seqs = [synth.synth_utt(s)[0] for s in seeds]
+  res = pmap(_predict_worker, [(d, s, {}) for s in seqs], jobs)
+  np.savez_compressed(
+      os.path.join(GOLD, 'synth500_bench.npz'), seeds=np.array(seeds),
+      labels=np.stack([r[0] for r in res]), ref_seconds=np.array([r[1] for r in res]))
+  print('synth500_bench ref seconds', [r[1] for r in res])
+
+
+def make_small500(jobs):
+  """D=64 / H=128 model on four 500-frame utterances: the long-utterance pin for the small kernel shape."""
+  d = dict(np.load(os.path.join(GOLD, 'model_small.npz')))
+  seeds = [7000 + u for u in range(4)]
+  seqs = [synth.synth_utt(s, n_frames=500, dim=64, n_spk=4, noise=0.08)[0] for s in seeds]
+  res = pmap(_predict_worker, [(d, s, {}) for s in seqs], jobs)
+  np.savez_compressed(
+      os.path.join(GOLD, 'small500.npz'), seeds=np.array(seeds),
+      labels=np.stack([r[0] for r in res]), ref_seconds=np.array([r[1] for r in res]))
+  print('small500 ref seconds', [r[1] for r in res])
+
+
+FIT_TRAJ_CASES = [
+    # name, seed, model kwargs, training kwargs
+    ('d1_b16', 21, dict(), dict(batch_size=16)),
+    ('d1_b48', 22, dict(), dict(batch_size=48)),
+    ('d2_b16', 23, dict(rnn_depth=2, rnn_dropout=0.0), dict(batch_size=16)),
+]
+
+
+def make_fit_traj():
+  """Loss trajectory of the reference's own fit() (uisrnn.py:172-313, 315-386): 20 iterations, D=64 / H=128.
+  The three loss terms of every iteration are recorded by wrapping (not replacing) the reference's
+  loss_func functions; initial and final parameters are stored so that the repo's fit() can be started from
+  the same point and compared ("loss1 trajectory vs oracle with identical RNG stream")."""
+  from uisrnn import loss_func as ref_loss
+  out = {'names': np.array([c[0] for c in FIT_TRAJ_CASES])}
+  for name, seed, mkw, tkw in FIT_TRAJ_CASES:
+    seed_all(seed)
+    m, t, _ = ref_args(observation_dim=64, rnn_hidden_size=128, train_iteration=20, learning_rate=1e-3,
+                       num_permutations=4, **mkw, **tkw)
+    seqs, ids = synth.synth_training_set(7100 + seed, 40, n_frames=60, dim=64, n_spk=3, noise=0.08)
+    model = ref.UISRNN(m)
+    init = model_to_dict_partial(model)
+    rec = {'l1': [], 'l2': [], 'l3': []}
+    orig = (ref_loss.weighted_mse_loss, ref_loss.sigma2_prior_loss, ref_loss.regularization_loss)
+
+    def wrap(fn, key):
+      def inner(*a, **k):
+        v = fn(*a, **k)
+        rec[key].append(float(v.detach()))
+        return v
+      return inner
+    ref_loss.weighted_mse_loss = wrap(orig[0], 'l1')
+    ref_loss.sigma2_prior_loss = wrap(orig[1], 'l2')
+    ref_loss.regularization_loss = wrap(orig[2], 'l3')
+    try:
+      seed_all(seed + 1000)   # the RNG state fit() starts from (shuffle, permutations, batch draws)
+      model.fit(seqs, ids, t)
+    finally:
+      ref_loss.weighted_mse_loss, ref_loss.sigma2_prior_loss, ref_loss.regularization_loss = orig
+    final = model_to_dict(model)
+    assert len(rec['l1']) == 20
+    out[name + '_args'] = np.array([seed, int(mkw.get('rnn_depth', 1)), tkw['batch_size']])
+    out[name + '_losses'] = np.array([rec['l1'], rec['l2'], rec['l3']], dtype=np.float64).T
+    for k, v in init.items():
+      out['{}_init_{}'.format(name, k)] = v
+    for k, v in final.items():
+      out['{}_final_{}'.format(name, k)] = v
+    print(name, 'loss1', rec['l1'][:3], '...', rec['l1'][-1], 'transition_bias', model.transition_bias)
+  np.savez_compressed(os.path.join(GOLD, 'fit_traj.npz'), **out)
+
+
+def model_to_dict_partial(model):
+  """model_to_dict for a model whose transition_bias is still None (before fit)."""
+  tb, model.transition_bias = model.transition_bias, 0.5
+  try:
+    d = model_to_dict(model)
+  finally:
+    model.transition_bias = tb
+  d.pop('transition_bias')
+  return {k: np.array(v) for k, v in d.items()}
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--only', default=None)
@@ -359,7 +450,9 @@ def main():
   steps = [('model_toy100', make_model_toy100), ('toy_test', lambda: make_toy_test(a.jobs)),
            ('synth500', lambda: make_synth500(a.jobs)), ('model_small', make_model_small),
            ('small_cases', lambda: make_small_cases(a.jobs)), ('model_small_d2', make_model_small_d2),
-           ('depth2_cases', lambda: make_depth2_cases(a.jobs)), ('ref_checkpoint', make_ref_checkpoint)]
+           ('depth2_cases', lambda: make_depth2_cases(a.jobs)), ('ref_checkpoint', make_ref_checkpoint),
+           ('synth500_bench', lambda: make_synth500_bench(a.jobs)), ('small500', lambda: make_small500(a.jobs)),
+           ('fit_traj', make_fit_traj)]
   for name, fn in steps:
     if a.only and name not in a.only.split(','):
       continue

@@ -228,3 +228,20 @@ def test_persistent_recurrence_kernels_match_per_step_launches(monkeypatch):
   for name in want:
     assert _rel(got[name], want[name]) < 2e-5, name
   persistent.close(); stepwise.close()
+
+
+@pytest.mark.parametrize('name', ['d1_b16'])
+def test_native_fit_follows_reference_trajectory(name):
+  """SURVEY 8(d) config 4 criterion: the device trainer (csrc/uis_train.cu), started from the reference's initial
+  parameters with the reference's RNG stream, follows the loss trajectory of the UNMODIFIED reference's fit()
+  (tests/golden/fit_traj.npz): first 20 iterations, every loss term, relative error <= 1e-3; the parameters it
+  ends at agree with the reference's to 1e-4."""
+  from fit_traj import run_case
+  losses, want, model, final = run_case(name, enable_cuda=True)
+  assert model.last_fit_backend == 'native'
+  assert losses.shape == want.shape == (20, 3)
+  assert np.max(np.abs(losses - want) / np.maximum(1.0, np.abs(want))) < 1e-3
+  sd = {k: v.cpu().numpy() for k, v in model.rnn_model.state_dict().items()}
+  assert np.max(np.abs(sd['linear_mean2.weight'] - final['w2'])) < 1e-4
+  assert np.max(np.abs(sd['gru.weight_hh_l0'] - final['weight_hh_l0'])) < 1e-4
+  assert np.max(np.abs(model.sigma2.detach().cpu().numpy() - final['sigma2'])) < 1e-5

@@ -204,3 +204,19 @@ def test_reads_reference_written_checkpoint_and_writes_the_same_format(tmp_path)
   for k, v in a['rnn_state_dict'].items():
     assert torch.equal(v, b['rnn_state_dict'][k])
   assert np.array_equal(a['sigma2'], b['sigma2']) and np.array_equal(a['rnn_init_hidden'], b['rnn_init_hidden'])
+
+
+@pytest.mark.parametrize('name', ['d1_b16', 'd1_b48', 'd2_b16'])
+def test_fit_reproduces_reference_trajectory_cpu(name):
+  """SURVEY 8(d) config 4 criterion on the CPU device: with the reference's RNG stream and initial parameters,
+  fit() follows the reference's own loss trajectory (20 iterations, all three loss terms) and ends at the
+  reference's parameters (tests/golden/fit_traj.npz, written by the unmodified reference)."""
+  from fit_traj import run_case
+  losses, want, model, final = run_case(name, enable_cuda=False)
+  assert losses.shape == want.shape == (20, 3)
+  assert np.max(np.abs(losses - want) / np.maximum(1.0, np.abs(want))) < 1e-4
+  assert abs(model.transition_bias - float(final['transition_bias'])) < 1e-12
+  sd = model.rnn_model.state_dict()
+  assert np.max(np.abs(sd['linear_mean2.weight'].numpy() - final['w2'])) < 2e-5
+  assert np.max(np.abs(sd['gru.weight_hh_l0'].numpy() - final['weight_hh_l0'])) < 2e-5
+  assert np.max(np.abs(model.sigma2.detach().numpy() - final['sigma2'])) < 2e-6

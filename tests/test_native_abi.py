@@ -27,9 +27,15 @@ def test_header_symbols_are_exported(lib):
     assert getattr(cdll, name) is not None
 
 
+def native_version():
+  header = open(os.path.join(ROOT, 'include', 'uisrnn_b200.h')).read()
+  return int(re.search(r'#define UIS_ABI_VERSION (\d+)', header).group(1))
+
+
 def test_version_and_error_string(lib):
-  cdll, _ = lib
-  assert cdll.uis_version() == 1
+  cdll, native = lib
+  assert native.UIS_ABI_VERSION == native_version()
+  assert cdll.uis_version() == native_version()
   assert isinstance(cdll.uis_last_error(), bytes)
 
 

@@ -80,3 +80,22 @@ def test_input_validation_matches_reference():
     uis_oracle.predict_single(m, np.zeros(64))
   with pytest.raises(TypeError):
     uis_oracle.predict(m, 'nope')
+
+
+def test_small500_matches_reference():
+  """500-frame utterances (1000 beam steps) with the D=64 / H=128 model: the long-utterance pin of the oracle."""
+  from uisrnn_b200.synth import synth_utt
+  g = np.load(GOLDEN + '/small500.npz')
+  m = oracle_model('model_small.npz')
+  for seed, want in list(zip(g['seeds'], g['labels']))[:2]:
+    x = synth_utt(int(seed), n_frames=500, dim=64, n_spk=4, noise=0.08)[0]
+    assert uis_oracle.predict_single(m, x) == want.tolist()
+
+
+def test_bench_utterance_matches_reference():
+  """One utterance of bench.py's own workload (seed 100000), default shape, against the reference's labels."""
+  from uisrnn_b200.synth import synth_utt
+  g = np.load(GOLDEN + '/synth500_bench.npz')
+  m = oracle_model('model_toy100.npz')
+  assert int(g['seeds'][0]) == 100000
+  assert uis_oracle.predict_single(m, synth_utt(100000)[0]) == g['labels'][0].tolist()

@@ -487,7 +487,8 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
   if (!(transition_bias > 0.0 && transition_bias < 1.0))
     return fail(UIS_ERR_INVALID, "transition_bias must be in (0,1), got %g", transition_bias);
   if (!(crp_alpha > 0.0)) return fail(UIS_ERR_INVALID, "crp_alpha must be > 0");
-  CU(cudaSetDevice(device));
+  uis::DeviceGuard device_guard_(device);
+  CU(device_guard_.status);
   uis_model* m = new uis_model();
   m->device = device; m->D = D; m->H = H; m->depth = depth; m->p0 = transition_bias; m->alpha = crp_alpha;
   int rc = 0;
@@ -565,7 +566,7 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
 
 int uis_model_destroy(uis_model* m) {
   if (!m) return 0;
-  cudaSetDevice(m->device);
+  uis::DeviceGuard device_guard_(m->device);
   DevBuf* bufs[] = {&m->wih_t, &m->whh_t, &m->w1_t, &m->w2_t, &m->bih, &m->bhh, &m->b1, &m->b2, &m->wvec, &m->mean0,
                     &m->hidden0, &m->wih_up_t, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
                     &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
@@ -580,7 +581,8 @@ int uis_model_destroy(uis_model* m) {
 
 int uis_model_constants(uis_model* m, float* mean0, float* hidden0) {
   if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
-  CU(cudaSetDevice(m->device));
+  uis::DeviceGuard device_guard_(m->device);
+  CU(device_guard_.status);
   if (mean0) CU(cudaMemcpy(mean0, m->mean0.p, m->D * 4, cudaMemcpyDeviceToHost));
   if (hidden0) CU(cudaMemcpy(hidden0, m->hidden0.p, (size_t)m->depth * m->H * 4, cudaMemcpyDeviceToHost));
   return 0;
@@ -597,7 +599,8 @@ int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_of
   Plan pl;
   if (int rc = make_plan(m, frame_offsets, U, opts, &pl, taps != nullptr)) return rc;
   if (U > 0 && pl.rows > 0 && (!x_dev || !labels_dev)) return fail(UIS_ERR_INVALID, "null device buffer");
-  CU(cudaSetDevice(m->device));
+  uis::DeviceGuard device_guard_(m->device);
+  CU(device_guard_.status);
   return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, static_cast<cudaStream_t>(stream));
 }
 
@@ -613,7 +616,8 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
   }
   Plan pl;
   if (int rc = make_plan(m, off.data(), U, opts, &pl, taps != nullptr)) return rc;
-  CU(cudaSetDevice(m->device));
+  uis::DeviceGuard device_guard_(m->device);
+  CU(device_guard_.status);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = m->D;
   const size_t n = (size_t)pl.rows * D;
@@ -644,7 +648,8 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
 
 int uis_get_stats(uis_model* m, uis_stats* out) {
   if (!m || !out) return fail(UIS_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(m->device));
+  uis::DeviceGuard device_guard_(m->device);
+  CU(device_guard_.status);
   const int rc = collect(m);
   *out = m->stats;
   return rc;

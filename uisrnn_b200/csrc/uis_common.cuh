@@ -6,6 +6,23 @@
 
 namespace uis {
 
+// Host side: every C entry point runs on its handle's device and puts the caller's current device back on
+// exit (a handle may be used -- or garbage-collected -- from a thread whose current device is another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    status = (prev == device) ? cudaSuccess : cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int now = -1;
+    if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

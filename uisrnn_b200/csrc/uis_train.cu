@@ -778,7 +778,8 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
   if (!out || !params || !hp) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   *out = nullptr;
   if (D < 1 || H < 1 || H > 4096 || D > 4096) return uis::api_fail(UIS_ERR_INVALID, "bad shape");
-  CUT(cudaSetDevice(device));
+  uis::DeviceGuard device_guard_(device);
+  CUT(device_guard_.status);
   uis_trainer* t = new uis_trainer();
   t->device = device; t->D = D; t->H = H; t->hp = *hp;
   const int sizes[SEG_COUNT] = {3 * H * D, 3 * H * H, 3 * H, 3 * H, H * H, H, D * H, D, H, D};
@@ -816,7 +817,7 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
 
 int uis_trainer_destroy(uis_trainer* t) {
   if (!t) return 0;
-  cudaSetDevice(t->device);
+  uis::DeviceGuard device_guard_(t->device);
   uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
                        &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
                        &t->partial, &t->skpart, &t->gemm_partial, &t->loss_hist};
@@ -893,7 +894,8 @@ int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths
                      float* losses_out /*[3] host*/, void* stream) {
   if (!t || !x_host || !lengths) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   if (int rc = check_lengths(lengths, B, L)) return rc;
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   return run_iteration(t, lengths, B, L, mode, losses_out, static_cast<cudaStream_t>(stream), x_host, nullptr);
 }
 
@@ -909,7 +911,8 @@ int uis_trainer_set_corpus(uis_trainer* t, const double* rows, int64_t n_rows, c
     if (index[i] < 0 || index[i] >= n_rows) return uis::api_fail(UIS_ERR_INVALID, "corpus index out of range");
   for (int32_t k = 0; k < n_sub; ++k)
     if (offsets[k + 1] < offsets[k]) return uis::api_fail(UIS_ERR_INVALID, "corpus offsets must be non-decreasing");
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   const size_t n = (size_t)n_rows * t->D;
   if (int rc = t->corpus.ensure(n)) return rc;
   double* tmp = nullptr;
@@ -949,7 +952,8 @@ int uis_trainer_step_corpus(uis_trainer* t, const int32_t* chosen, int B, int mo
     cols.length[b] = lengths[b];
   }
   if (int rc = check_lengths(lengths, B, lengths[0])) return rc;
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   return run_iteration(t, lengths, B, lengths[0], mode, losses_out, static_cast<cudaStream_t>(stream), nullptr, &cols);
 }
 
@@ -1117,7 +1121,8 @@ extern "C" {
 int uis_trainer_losses(uis_trainer* t, int count, float* out) {
   if (!t || !out || count < 0) return uis::api_fail(UIS_ERR_INVALID, "bad argument");
   if (count > t->calls || count > t->hist_cap) return uis::api_fail(UIS_ERR_INVALID, "only %lld steps recorded", t->calls);
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   CUT(cudaDeviceSynchronize());
   if (int rc = seq_check(t)) return rc;
   for (int i = 0; i < count; ++i) {
@@ -1133,7 +1138,8 @@ int64_t uis_trainer_comm_size(uis_trainer* t) { return t ? (int64_t)t->sigma_beg
 
 int uis_trainer_comm_export(uis_trainer* t, float* dev_buf, void* stream) {
   if (!t || !dev_buf) return uis::api_fail(UIS_ERR_INVALID, "null argument");
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUT(cudaMemcpyAsync(dev_buf, t->grads.p, (size_t)t->sigma_begin * 4, cudaMemcpyDeviceToDevice, st));
   CUT(cudaMemcpyAsync(dev_buf + t->sigma_begin, t->small, (size_t)(2 * t->D + 1) * 4, cudaMemcpyDeviceToDevice, st));
@@ -1142,7 +1148,8 @@ int uis_trainer_comm_export(uis_trainer* t, float* dev_buf, void* stream) {
 
 int uis_trainer_comm_apply(uis_trainer* t, const float* dev_buf, void* stream) {
   if (!t || !dev_buf) return uis::api_fail(UIS_ERR_INVALID, "null argument");
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = t->D;
   CUT(cudaMemcpyAsync(t->grads.p, dev_buf, (size_t)t->sigma_begin * 4, cudaMemcpyDeviceToDevice, st));
@@ -1159,7 +1166,8 @@ int uis_trainer_comm_apply(uis_trainer* t, const float* dev_buf, void* stream) {
 // what: 0 = parameters, 1 = gradients of the last step.  out[10] host buffers (any may be NULL).
 int uis_trainer_get(uis_trainer* t, int what, float* const* out) {
   if (!t || !out) return uis::api_fail(UIS_ERR_INVALID, "null argument");
-  CUT(cudaSetDevice(t->device));
+  uis::DeviceGuard device_guard_(t->device);
+  CUT(device_guard_.status);
   CUT(cudaDeviceSynchronize());
   if (int rc = seq_check(t)) return rc;
   const float* src = what == 0 ? t->params.p : t->grads.p;

@@ -5,6 +5,7 @@ fallback here: if the shared library is missing or a call fails, an exception is
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -19,6 +20,7 @@ UIS_ERR_CUDA = -3
 UIS_ERR_OVERFLOW = -4
 UIS_ERR_NOMEM = -5
 UIS_ERR_CAPACITY = -6
+UIS_ABI_VERSION = 2  # include/uisrnn_b200.h
 
 
 class NativeError(RuntimeError):
@@ -89,6 +91,20 @@ def load_library():
   lib = C.CDLL(LIB_PATH)
   fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
   lib.uis_version.restype = C.c_int
+  # the structs below are laid out for exactly one ABI version: a stale binary (the .so is built out of band and
+  # git-ignored) must not be driven with mismatching layouts
+  if lib.uis_version() != UIS_ABI_VERSION:
+    raise NativeError(UIS_ERR_INVALID, '{} reports ABI version {}, this binding needs {}: rebuild it (python -c '
+                      '"import __graft_entry__ as g; g.build()")'.format(LIB_PATH, lib.uis_version(), UIS_ABI_VERSION))
+  if not os.environ.get('UISRNN_B200_LIB'):
+    try:
+      from . import build as _build
+      if _build.is_stale():
+        import warnings
+        warnings.warn('libuisrnn_b200.so is older than its sources (uisrnn_b200/csrc); rebuild with '
+                      '__graft_entry__.build()', RuntimeWarning)
+    except OSError:
+      pass
   lib.uis_last_error.restype = C.c_char_p
   lib.uis_model_create.restype = C.c_int
   lib.uis_model_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int] + \
@@ -159,6 +175,7 @@ class NativeModel:
     self.D = int(np.asarray(w['w2']).shape[0])
     self.device = device
     self.depth = depth
+    self.lock = threading.Lock()  # callers sharing this handle between threads serialise on it
     H, D = self.H, self.D
     layers = range(depth)
     for l in layers:  # PyTorch nn.GRU layouts: layer 0 sees the observation, layer l >= 1 sees layer l-1

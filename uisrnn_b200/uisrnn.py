@@ -184,6 +184,7 @@ class UISRNN:
       index_lists, seq_lengths = utils.resize_indices(train_cluster_id, args.num_permutations)
       self._fit_native(train_sequence, index_lists, seq_lengths, args)
       return
+    self.last_fit_backend = 'torch'
     sub_sequences, seq_lengths = utils.resize_sequence(
         sequence=train_sequence, cluster_id=train_cluster_id, num_permutations=args.num_permutations)
     batch = None
@@ -268,6 +269,8 @@ class UISRNN:
                'train_sigma2': self.estimate_sigma2}
     trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
     self.last_training_losses = []
+    self.last_training_loss_terms = []  # [iteration] -> (negative log likelihood, sigma2 prior, regularisation)
+    self.last_fit_backend = 'native'
     comm = torch.zeros(trainer.comm_size(), dtype=torch.float32, device=self.device) if world > 1 else None
     sampler = utils.BatchSampler(seq_lengths, args.batch_size)
     try:
@@ -293,6 +296,7 @@ class UISRNN:
         if log_now or pending == 4096:
           recent = trainer.losses(pending)
           self.last_training_losses.extend(float(v) for v in recent[:, 0])
+          self.last_training_loss_terms.extend(tuple(float(v) for v in row) for row in recent)
           pending = 0
           if log_now:
             loss1, loss2, loss3 = (float(v) for v in recent[-1])
@@ -342,8 +346,14 @@ class UISRNN:
 
   # ------------------------------------------------------------------ inference
   def _fingerprint(self):
+    """Identity of the parameter values the device-side twin was built from.  `_version` does not move on
+    edits through `.data` (an idiom the reference's own tests use), so a cheap content checksum -- sum and
+    sum of squares per tensor, one fused reduction -- is part of the key."""
     tensors = list(self.rnn_model.parameters()) + [self.rnn_init_hidden, self.sigma2]
-    return (tuple((t.data_ptr(), t._version) for t in tensors), self.transition_bias, self.crp_alpha)
+    with torch.no_grad():
+      sums = torch.stack([torch.stack((t.detach().double().sum(), (t.detach().double() ** 2).sum())) for t in tensors])
+    return (tuple((t.data_ptr(), t._version) for t in tensors), tuple(sums.flatten().tolist()),
+            self.transition_bias, self.crp_alpha)
 
   def export_weights(self):
     """Weights as float32 numpy arrays in the layout libuisrnn_b200.so / the oracle expect."""
@@ -378,8 +388,9 @@ class UISRNN:
     kcap = _DEFAULT_KCAP
     while True:
       try:
-        labels = model.predict(sequences, beam_size=args.beam_size, look_ahead=args.look_ahead,
-                               test_iteration=args.test_iteration, kcap=kcap)
+        with model.lock:  # a uis_model handle (one workspace) is not re-entrant
+          labels = model.predict(sequences, beam_size=args.beam_size, look_ahead=args.look_ahead,
+                                 test_iteration=args.test_iteration, kcap=kcap)
         return [lab.tolist() for lab in labels]
       except native.NativeError as err:
         if err.code != native.UIS_ERR_OVERFLOW or kcap >= 1024:
@@ -468,8 +479,9 @@ class _DeviceTwin:
     kcap = _DEFAULT_KCAP
     while True:
       try:
-        labels = model.predict(sequences, beam_size=args.beam_size, look_ahead=args.look_ahead,
-                               test_iteration=args.test_iteration, kcap=kcap)
+        with model.lock:
+          labels = model.predict(sequences, beam_size=args.beam_size, look_ahead=args.look_ahead,
+                                 test_iteration=args.test_iteration, kcap=kcap)
         return [lab.tolist() for lab in labels]
       except native.NativeError as err:
         if err.code != native.UIS_ERR_OVERFLOW or kcap >= 1024:
