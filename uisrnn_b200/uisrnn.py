@@ -351,8 +351,16 @@ class UISRNN:
     sum of squares per tensor, one fused reduction -- is part of the key."""
     tensors = list(self.rnn_model.parameters()) + [self.rnn_init_hidden, self.sigma2]
     with torch.no_grad():
-      sums = torch.stack([torch.stack((t.detach().double().sum(), (t.detach().double() ** 2).sum())) for t in tensors])
-    return (tuple((t.data_ptr(), t._version) for t in tensors), tuple(sums.flatten().tolist()),
+      by_device = {}  # the parameters need not share a device (callers assign rnn_init_hidden / sigma2 freely)
+      for i, t in enumerate(tensors):
+        d = t.detach().double()
+        by_device.setdefault(t.device, []).append((i, torch.stack((d.sum(), (d * d).sum()))))
+      sums = [None] * len(tensors)
+      for parts in by_device.values():  # one reduction batch and one device -> host copy per device
+        flat = torch.stack([s for _, s in parts]).cpu().tolist()
+        for (i, _), pair in zip(parts, flat):
+          sums[i] = tuple(pair)
+    return (tuple((t.data_ptr(), t._version) for t in tensors), tuple(sums),
             self.transition_bias, self.crp_alpha)
 
   def export_weights(self):
