@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UIS_ABI_VERSION 2
+#define UIS_ABI_VERSION 3
 
 typedef enum uis_status {
   UIS_OK = 0,
@@ -50,11 +50,15 @@ typedef struct uis_predict_opts {
                              when look_ahead >= 2)                                             */
   int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
   int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
-                             0 = auto (2 when U >= 2 * CTAs, else 1), max 4                    */
+                             0 = auto (FFMA engine: 2 when U >= 2 * CTAs, else 1, max 4;
+                             tensor-core engine: up to columns / 8 = 6, max 8)                  */
   int32_t cluster;        /* CTAs per utterance (thread-block cluster, latency mode for few
                              utterances; default shape, depth 1, look_ahead 1): 0 = auto (4 or 2
                              when U * cluster <= CTAs), -1 = off, 2 / 4 / 8 = forced               */
-  int32_t reserved;
+  int32_t engine;         /* matrix engine of the look_ahead-1 beam kernel: 0 = auto (tensor cores
+                             when some CTA gets more than one utterance), 1 = fp32 FFMA kernels,
+                             2 = tcgen05 tensor-core pass (fp16 hi/lo split operands, fp32-grade;
+                             depth 1, hidden/dim multiples of 128; kcap defaults to 16)          */
 } uis_predict_opts;
 
 /* Optional per-call debug / parity taps.  Any pointer may be NULL.  All are HOST buffers
@@ -89,6 +93,8 @@ typedef struct uis_stats {
   float beam_ms;           /* device time of the persistent beam-search kernel                 */
   int32_t lanes;           /* lanes per CTA used                                               */
   int32_t cluster;   /* thread-block cluster size the last call used (1 = none) */
+  int32_t engine;          /* 1 = FFMA kernels, 2 = tensor-core pass                            */
+  int32_t tc_columns;      /* tensor-core pass: columns per weight pass (0 otherwise)           */
   int64_t phase_cycles[10]; /* SM cycles summed over CTAs: [0] re-pack (P4), [1] gather, [2] GRU pass,
                                [3] W1 pass, [4] W2 pass, [5] advance/back-track, [6] frame landing
                                (P0), [7] scoring (P1), [8] ranking (P2), [9] column/slot assignment (P3) */

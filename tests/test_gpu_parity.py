@@ -115,7 +115,7 @@ def test_many_utterances_are_independent_of_batching(toy_model):
   together = toy_model.predict(xs)
   few_ctas = toy_model.predict(xs, n_ctas=3)
   for lanes in (1, 2, 3):  # lanes share weight passes only; results must not depend on them
-    got = toy_model.predict(xs, n_ctas=5, lanes=lanes)
+    got = toy_model.predict(xs, n_ctas=5, lanes=lanes, engine=1)
     assert toy_model.stats()["lanes"] == min(lanes, 2)  # SMEM limits lanes to 2 at kcap=32
     assert all(a.tolist() == b.tolist() for a, b in zip(got, together)), 'lanes=%d' % lanes
   for i in (0, 7, 39):

@@ -7,7 +7,7 @@ Variants are forced through the C ABI's `lanes` / `cluster` options (`include/ui
   lanes=2 cluster=-1   uis_beam_kernel<H,D,false,false>, two utterances per CTA sharing each weight pass (bench path)
   lanes=1 cluster=-1   the same kernel, one utterance per CTA
   lanes=0 cluster=0    automatic choice (few utterances -> thread-block-cluster kernel)
-  tc=1                 tensor-core pass (tcgen05) where it is instantiated
+  engine=2             the tensor-core pass (tcgen05): tests/test_gpu_tensorcore.py
 """
 import numpy as np
 import pytest
@@ -16,7 +16,8 @@ from helpers import GOLDEN, load_weights, uis_oracle
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [dict(lanes=2, cluster=-1), dict(lanes=1, cluster=-1), dict(lanes=0, cluster=0), dict(lanes=4, cluster=-1)]
+VARIANTS = [dict(lanes=2, cluster=-1, engine=1), dict(lanes=1, cluster=-1, engine=1), dict(lanes=0, cluster=0, engine=1),
+            dict(lanes=4, cluster=-1, engine=1)]
 
 
 @pytest.fixture(scope='module')
@@ -101,19 +102,19 @@ def test_mid_shape_matches_oracle(native, opts):
 
 def test_full_bench_batch_first_median_last(toy_model):
   """One call with bench.py's whole per-GPU batch (296 utterances x 500 frames, automatic options = what the bench
-  launches): the utterances the reference decoded (first six, median two, last two) must come out identical, and
+  launched in round 1 -- the FFMA engine with two lanes): the utterances the reference decoded (first six, median two, last two) must come out identical, and
   the device-resident entry point must agree with the host entry point on every utterance."""
   import torch
   from uisrnn_b200.synth import synth_utt
   seeds, _, want = _bench_golden()
   U = 296
   xs = [synth_utt(100000 + u)[0] for u in range(U)]
-  got = toy_model.predict(xs)
+  got = toy_model.predict(xs, engine=1)
   st = toy_model.stats()
-  assert st['lanes'] == 2 and st['cluster'] == 1 and st['utterances'] == U
+  assert st['lanes'] == 2 and st['cluster'] == 1 and st['utterances'] == U and st['engine'] == 1
   for s, w in zip(seeds, want):
     assert got[s - 100000].tolist() == w, 'utterance %d of the bench batch' % (s - 100000)
   x_dev = torch.from_numpy(np.concatenate(xs).astype(np.float32)).cuda()
   lab_dev = torch.empty(U * 500, dtype=torch.int32, device='cuda')
-  toy_model.predict_device(x_dev.data_ptr(), np.arange(U + 1, dtype=np.int64) * 500, lab_dev.data_ptr())
+  toy_model.predict_device(x_dev.data_ptr(), np.arange(U + 1, dtype=np.int64) * 500, lab_dev.data_ptr(), engine=1)
   assert np.array_equal(lab_dev.cpu().numpy(), np.concatenate(got))

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header(lib):
   _, native = lib
   assert ctypes.sizeof(native.PredictOpts) == 8 * 4
   assert ctypes.sizeof(native.DebugTaps) == 8 + 8 * 8
-  assert ctypes.sizeof(native.Stats) == 7 * 8 + 2 * 4 + 2 * 4 + 2 * 4 + 10 * 8
+  assert ctypes.sizeof(native.Stats) == 7 * 8 + 2 * 4 + 2 * 4 + 4 * 4 + 10 * 8  # + engine, tc_columns (ABI 3)
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu(lib):
@@ -67,3 +67,22 @@ def test_sass_uses_tma_and_packed_fma():
   # register re-balancing of the warp-specialised CTA, and the cluster (latency) mode: cluster barrier at start-up,
   # remote mbarrier arrives (the .RED form) for the distributed-shared-memory exchange
   assert 'USETMAXREG' in sass and 'UCGABAR_ARV' in sass and 'SYNCS.ARRIVE.TRANS64.RED' in sass
+
+
+def test_sass_uses_tcgen05_tmem_and_tensor_map_tma():
+  """The tensor-core engine must be the real thing: tcgen05.mma (UTCHMMA), TMEM loads (LDTM) and tensor-map TMA
+  (UTMALDG) inside the uis_beam_kernel<.., columns> instantiations -- B200_PROFILING.md, "What proves a
+  Blackwell-native kernel"."""
+  import shutil
+  import subprocess
+  tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+  if not os.path.exists(tool):
+    pytest.skip('cuobjdump not available')
+  from uisrnn_b200 import native
+  sass = subprocess.run([tool, '-sass', native.LIB_PATH], capture_output=True, text=True).stdout
+  start = sass.find('uis_beam_kernelILi512ELi256ELb0ELb0ELi48EE')
+  assert start >= 0, 'tensor-core instantiation missing'
+  end = sass.find('Function :', start + 10)
+  body = sass[start:end if end > 0 else len(sass)]
+  for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTCBAR'):
+    assert mnemonic in body, mnemonic

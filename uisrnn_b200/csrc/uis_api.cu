@@ -2,6 +2,8 @@
 // weight re-layout at model creation, workspace management, utterance scheduling (longest
 // first), kernel launches.  No PyTorch types, no CPU compute fallback: if the kernels are not
 // instantiated for a shape the call fails with UIS_ERR_UNSUPPORTED.
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -87,6 +89,11 @@ struct uis_model {
   // weights, k-major
   DevBuf wih_t, whh_t, w1_t, w2_t, bih, bhh, b1, b2, wvec, mean0, hidden0;
   DevBuf wih_up_t;  // [depth-1][H][3H]; whh_t is [depth][H][3H]; bih / bhh are [depth][3H]
+  // tensor-core pass (uis_beam_tc.cuh): fp16 hi/lo planes of [W_hh; W1; W2] behind a tensor map, scales
+  DevBuf tc_planes, tc_scratch;
+  alignas(64) CUtensorMap tc_map;
+  bool tc_ready = false;
+  float tc_sh = 0, tc_sa = 0, tc_inv_hh = 0, tc_inv_1 = 0, tc_inv_2 = 0;
   // log tables
   DevBuf logn, logtot;
   int log_cap = 0;
@@ -179,6 +186,88 @@ std::vector<float> transpose(const std::vector<float>& w, int rows, int cols) {
   return t;
 }
 
+// ---- tensor-core pass: one-off weight preparation --------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// largest power of two s with bound * s <= 2^14 (fp16 keeps 11 significant bits down to 2^-14; |hi| stays < 65504)
+float tc_pow2_scale(double bound) {
+  if (!(bound > 0.0) || !std::isfinite(bound)) return 0.f;
+  int e = 0;
+  std::frexp(16384.0 / bound, &e);   // 16384 / bound = f * 2^e, f in [0.5, 1)
+  e -= 1;                            // 2^e <= 16384 / bound
+  if (e > 40) e = 40;
+  if (e < -40) return 0.f;
+  return std::ldexp(1.0f, e);
+}
+
+// Splits w * scale into fp16 hi + lo (22 significant bits) -- the A operand planes of the tcgen05 pass.
+void tc_split(const std::vector<float>& w, float scale, __half* hi, __half* lo) {
+  for (size_t i = 0; i < w.size(); ++i) {
+    const float v = w[i] * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// w_hh [3H,H], w1 [H,H], w2 [D,H] are the row-major (= K-major) PyTorch tensors; hidden0 [H] = CoreRNN(0, h0).
+// Leaves tc_ready false (the FFMA kernels serve the model) when the shape does not tile or a bound is not finite.
+int tc_prepare(uis_model* m, const std::vector<float>& w_hh, const std::vector<float>& w1, const std::vector<float>& b1,
+               const std::vector<float>& w2, const std::vector<float>& hidden0) {
+  const int H = m->H, D = m->D;
+  m->tc_ready = false;
+  if (m->depth != 1 || !uis::beam_tc_supported(H, D, 48)) return 0;
+  auto maxabs = [](const std::vector<float>& v) { double a = 0; for (float x : v) a = std::max(a, (double)std::fabs(x)); return a; };
+  // |h'| <= max(1, |h|) by induction (h' is a convex combination of h and tanh(.)), starting from hidden0
+  const double hmax = std::max(1.0, maxabs(hidden0));
+  double amax = 0;  // a = relu(W1 h' + b1):  |a_i| <= |b1_i| + hmax * sum_j |W1_ij|
+  for (int i = 0; i < H; ++i) {
+    double srow = 0;
+    for (int j = 0; j < H; ++j) srow += std::fabs(w1[(size_t)i * H + j]);
+    amax = std::max(amax, std::fabs((double)b1[i]) + hmax * srow);
+  }
+  const float s_hh = tc_pow2_scale(maxabs(w_hh)), s_1 = tc_pow2_scale(maxabs(w1)), s_2 = tc_pow2_scale(maxabs(w2));
+  const float s_h = tc_pow2_scale(hmax), s_a = tc_pow2_scale(std::max(amax, 1e-30));
+  if (s_hh == 0.f || s_1 == 0.f || s_2 == 0.f || s_h == 0.f || s_a == 0.f) return 0;
+  const size_t rows = (size_t)3 * H + H + D, n = rows * H;
+  std::vector<__half> planes(2 * n);  // [plane 0 = lo | plane 1 = hi][rows][H]
+  tc_split(w_hh, s_hh, planes.data() + n, planes.data());
+  {
+    std::vector<__half> hi((size_t)H * H), lo((size_t)H * H);
+    tc_split(w1, s_1, hi.data(), lo.data());
+    std::copy(lo.begin(), lo.end(), planes.begin() + (size_t)3 * H * H);
+    std::copy(hi.begin(), hi.end(), planes.begin() + n + (size_t)3 * H * H);
+  }
+  {
+    std::vector<__half> hi((size_t)D * H), lo((size_t)D * H);
+    tc_split(w2, s_2, hi.data(), lo.data());
+    std::copy(lo.begin(), lo.end(), planes.begin() + (size_t)4 * H * H);
+    std::copy(hi.begin(), hi.end(), planes.begin() + n + (size_t)4 * H * H);
+  }
+  if (int r = upload(m->tc_planes, planes.data(), planes.size() * sizeof(__half))) return r;
+  TensorMapEncodeFn encode = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", reinterpret_cast<void**>(&encode), cudaEnableDefault, &qres) !=
+          cudaSuccess || !encode || qres != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return 0;  // driver without tensor maps: the FFMA kernels serve the model
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)(2 * rows)};
+  const cuuint64_t gstr[1] = {(cuuint64_t)H * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&m->tc_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, m->tc_planes.p, gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 0;
+  m->tc_sh = s_h; m->tc_sa = s_a;
+  m->tc_inv_hh = 1.0f / (s_hh * s_h); m->tc_inv_1 = 1.0f / (s_1 * s_h); m->tc_inv_2 = 1.0f / (s_2 * s_a);
+  m->tc_ready = true;
+  return 0;
+}
+
 int ensure_log_tables(uis_model* m, int max_tn) {
   const int need = max_tn + 2;
   if (need <= m->log_cap) return 0;
@@ -196,6 +285,7 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
   int cluster = 1;  // CTAs per utterance (thread-block cluster size); 1 = one CTA per lane group
+  int tcn = 0;      // > 0: tensor-core beam kernel with this many columns per pass (uis_beam_tc.cuh)
   bool cluster_forced = false;
   int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
   long long rows;
@@ -208,11 +298,13 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
     return fail(UIS_ERR_INVALID, "beam_size, look_ahead and test_iteration must be >= 1");
   if (o->look_ahead > 8) return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d > 8 not supported", o->look_ahead);
   if (o->beam_size > 32) return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > 32 not supported", o->beam_size);
+  if (o->engine < 0 || o->engine > 2) return fail(UIS_ERR_INVALID, "engine must be 0 (auto), 1 (FFMA) or 2 (tensor cores)");
   pl->B = o->beam_size;
   pl->L = o->look_ahead;
   pl->T = o->test_iteration;
   const bool tree = pl->L > 1;
   pl->Kcap = o->kcap > 0 ? o->kcap : (tree ? 16 : 32);
+  pl->tcn = 0;
   if (pl->Kcap > 2047 || pl->B * pl->Kcap + pl->B + 1 > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
   if (tree && pl->Kcap > 255) return fail(UIS_ERR_UNSUPPORTED, "look_ahead >= 2 supports kcap <= 255");
   pl->P = pl->B * pl->Kcap + pl->B + 1;
@@ -228,7 +320,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   int ctas = o->n_ctas > 0 ? o->n_ctas : m->num_sms;
   // lanes (utterances advanced together by one CTA, sharing each weight pass): 2 when there is
   // enough work to keep every CTA's lanes busy, else 1 (latency mode); opts->lanes overrides.
-  int G = o->lanes > 0 ? std::min(o->lanes, (int)uis::kMaxLanes) : ((long long)U >= 2ll * ctas ? 2 : 1);
+  int G = o->lanes > 0 ? std::min(o->lanes, 4) : ((long long)U >= 2ll * ctas ? 2 : 1);
   if (tree) {
     // look-ahead tree kernel: one utterance per CTA; size the on-chip node / leaf arrays to what
     // shared memory allows (internal nodes : leaves ~ 1 : 8, the typical fan-out K+2)
@@ -248,8 +340,40 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
     pl->leaf_cap = 8 * ni;
     pl->P = pl->B * pl->Kcap + ni + pl->B + 1;
   } else {
-    while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
+    // Tensor-core engine (look_ahead 1, depth 1, 128-row-tileable shapes): the cost of a weight pass does not depend on
+    // the number of columns, so a CTA advances up to N / 8 utterances together (a lane needs ~6 columns per step,
+    // at most beam_size + 1).  Chosen automatically when some CTA gets more than one utterance; below that the
+    // one-lane FFMA kernel or the cluster (latency) mode is faster.  Its device tables default to 16 clusters per
+    // hypothesis (UIS_ERR_OVERFLOW asks the caller for more, as always).
+    if (o->engine != 1 && m->tc_ready && o->cluster <= 0) {
+      int N = 48;
+      if (const char* env = std::getenv("UISRNN_B200_TC_N")) N = std::atoi(env);
+      if (uis::beam_tc_supported(m->H, m->D, N)) {
+        const int kc = o->kcap > 0 ? o->kcap : 16;
+        int Gt = o->lanes > 0 ? std::min(o->lanes, (int)uis::kMaxLanes)
+                              : (int)std::min<long long>(N / 8, ((long long)U + ctas - 1) / std::max(ctas, 1));
+        Gt = std::max(Gt, 1);
+        while (Gt > 1 && uis::beam_tc_smem(m->H, m->D, N, pl->B, kc, Gt) > 227u * 1024u) --Gt;
+        const bool fits = uis::beam_tc_smem(m->H, m->D, N, pl->B, kc, Gt) <= 227u * 1024u &&
+                          pl->B * kc + pl->B + 1 <= 65535;
+        if (fits && (o->engine == 2 || (long long)U > ctas)) {
+          pl->tcn = N;
+          pl->Kcap = kc;
+          pl->P = pl->B * kc + pl->B + 1;
+          G = Gt;
+        } else if (o->engine == 2) {
+          return fail(UIS_ERR_UNSUPPORTED, "tensor-core engine: beam_size=%d kcap=%d does not fit in shared memory", pl->B, kc);
+        }
+      } else if (o->engine == 2) {
+        return fail(UIS_ERR_UNSUPPORTED, "tensor-core engine: no kernel for hidden=%d dim=%d columns=%d", m->H, m->D, N);
+      }
+    } else if (o->engine == 2) {
+      return fail(UIS_ERR_UNSUPPORTED, "tensor-core engine needs look_ahead 1, depth 1, hidden/dim multiples of 128 and no cluster mode");
+    }
+    if (!pl->tcn)
+      while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
   }
+  if (tree && o->engine == 2) return fail(UIS_ERR_UNSUPPORTED, "tensor-core engine: look_ahead must be 1");
   pl->G = G;
   pl->ctas = std::max(1, std::min(ctas, std::max((U + G - 1) / G, 1)));
   // Cluster (latency) mode: with fewer utterances than SMs, a thread-block cluster of 2/4/8 CTAs works on
@@ -257,7 +381,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   // that still gives every utterance its own cluster), -1 = off, 2/4/8 = forced; UISRNN_B200_CLUSTER=0 disables
   // the automatic choice.
   pl->cluster = 1;
-  if (!tree && U >= 1 && o->cluster >= 0 && !has_taps && m->depth == 1 && o->lanes <= 1) {
+  if (!tree && !pl->tcn && U >= 1 && o->cluster >= 0 && !has_taps && m->depth == 1 && o->lanes <= 1) {
     int cs = 0;
     if (o->cluster == 2 || o->cluster == 4 || o->cluster == 8) {
       cs = o->cluster;
@@ -288,6 +412,7 @@ size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
   b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->depth * m->H) * 4;    // slot pools
   b += (size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B * 4;  // back-pointers
   b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
+  if (pl.tcn) b += (size_t)pl.ctas * pl.tcn * m->H * 4;                 // a = relu(W1 h' + b1) between two products
   return b;
 }
 
@@ -328,6 +453,9 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
                             sizeof(unsigned)))
     return rc;
 
+  if (pl.tcn)
+    if (int rc = m->tc_scratch.ensure((size_t)pl.ctas * pl.tcn * H * sizeof(float))) return rc;
+
   CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(m->queue_stats.p, 0, 32 * sizeof(unsigned long long), st));
@@ -359,6 +487,12 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.stats = m->queue_stats.as<unsigned long long>() + 8;
   p.labels = labels_dev; p.status = m->status.as<int>();
   p.trace_utt = -1;
+  if (pl.tcn) {
+    p.tc_wmap = m->tc_map;
+    p.tc_sh = m->tc_sh; p.tc_sa = m->tc_sa;
+    p.tc_inv_hh = m->tc_inv_hh; p.tc_inv_1 = m->tc_inv_1; p.tc_inv_2 = m->tc_inv_2;
+    p.tc_scratch = m->tc_scratch.as<float>();
+  }
 
   long long trace_steps = 0;
   if (taps) {
@@ -402,10 +536,18 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
   int cluster_used = pl.cluster;
-  if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st)
-                         : dispatch_beam(H, D, p, pl.ctas, &cluster_used, pl.cluster_forced, st)))
+  if (pl.tcn) {
+    cudaError_t e = cudaSuccess;
+    if (!uis::launch_beam_tc(H, D, pl.tcn, p, pl.ctas, uis::beam_tc_smem(H, D, pl.tcn, pl.B, pl.Kcap, pl.G), st, &e))
+      return fail(UIS_ERR_UNSUPPORTED, "no tensor-core kernel for hidden=%d dim=%d columns=%d", H, D, pl.tcn);
+    if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "tensor-core beam kernel launch failed: %s", cudaGetErrorString(e));
+  } else if (int rc = (pl.L > 1 ? dispatch_tree(H, D, p, pl.ctas, st)
+                                : dispatch_beam(H, D, p, pl.ctas, &cluster_used, pl.cluster_forced, st))) {
     return rc;
+  }
   m->stats.cluster = cluster_used;
+  m->stats.engine = pl.tcn ? 2 : 1;
+  m->stats.tc_columns = pl.tcn;
   CU(cudaEventRecord(m->ev[2], st));
   m->stats.kernel_launches = 2;
   m->stats_pending = true;
@@ -553,6 +695,15 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     h0d.release();
+    if (depth == 1) {  // tensor-core pass: fp16 hi/lo planes of the untransposed (K-major) matrices + tensor map
+      std::vector<float> whh0, w1v, b1v, w2v, hid0((size_t)H);
+      if (int r = fetch(whh0, w_hh, (size_t)3 * H * H)) return r;
+      if (int r = fetch(w1v, w1, (size_t)H * H)) return r;
+      if (int r = fetch(b1v, b1, H)) return r;
+      if (int r = fetch(w2v, w2, (size_t)D * H)) return r;
+      CU(cudaMemcpy(hid0.data(), m->hidden0.p, (size_t)H * 4, cudaMemcpyDeviceToHost));
+      if (int r = tc_prepare(m, whh0, w1v, b1v, w2v, hid0)) return r;
+    }
     return 0;
   };
   rc = body();
@@ -571,7 +722,7 @@ int uis_model_destroy(uis_model* m) {
                     &m->hidden0, &m->wih_up_t, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
                     &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
                     &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
-                    &m->dbg_best_hidden, &m->dbg_best_blocks};
+                    &m->dbg_best_hidden, &m->dbg_best_blocks, &m->tc_planes, &m->tc_scratch};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : m->ev)
     if (e) cudaEventDestroy(e);

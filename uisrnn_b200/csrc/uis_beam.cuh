@@ -30,6 +30,7 @@
 //     only the winners' distinct source states go through the GRU.
 #pragma once
 #include "uis_common.cuh"
+#include "uis_beam_tc.cuh"
 
 namespace uis {
 
@@ -43,7 +44,7 @@ constexpr int kCPBeam = UIS_CP_BEAM;             // GRU columns per weight pass,
 constexpr int kCPCluster = 12;          // cluster (latency) mode: one lane per cluster, <= 12 columns per pass
 constexpr int kXchVals = 24;            // floats per thread and exchange round of the cluster K-split
 constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;
 constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
 
 struct TabEntry {
@@ -81,6 +82,11 @@ struct BeamParams {
   int U, B, Kcap, T, P, maxN, G;
   int L, node_cap, leaf_cap, maxTN, maxSteps;  // look_ahead >= 2 (uis_beam_tree.cuh) only
   int dbg_mode;  // 0 normal; 1 = stream the weights but skip the math (timing experiment, results invalid)
+  // tensor-core pass (uis_beam_tc.cuh): fp16 hi/lo weight planes [2 * (3H + H + D)][H] behind a tensor map
+  alignas(64) CUtensorMap tc_wmap;
+  float tc_sh, tc_sa;                  // power-of-two scales of the hidden columns and of a = relu(W1 h' + b1)
+  float tc_inv_hh, tc_inv_1, tc_inv_2; // 1 / (weight scale * operand scale) per matrix
+  float* tc_scratch;                   // [ctas][N][H]  a = relu(W1 h' + b1) between the W1 and the W2 product
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
   float* pool_hidden;  // [ctas*G][P][depth][H]
@@ -152,13 +158,20 @@ enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRAC
 // CTA scalars
 enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT };
 
-template <int H, int D, int kCP = kCPBeam, bool XCL = false>
+template <int H, int D, int kCP = kCPBeam, bool XCL = false, int TCN = 0>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   SmemLayout L;
   unsigned o = 0;
-  L.ring = o;  o += kStages * kStageBytes;
-  L.xa = o;    o += H * kCP * 4;
-  L.xb = o;    o += H * kCP * 4;
+  if constexpr (TCN > 0) {  // tensor-core pass: ring of 16 KB weight boxes, B operand (both 1024-byte aligned)
+    using TC = TcCfg<H, D, TCN>;
+    L.ring = o;  o += TC::STAGES * kTcBoxBytes;
+    L.xa = o;    o += TC::BOP_BYTES;
+    L.xb = o;
+  } else {
+    L.ring = o;  o += kStages * kStageBytes;
+    L.xa = o;    o += H * kCP * 4;
+    L.xb = o;    o += H * kCP * 4;
+  }
   L.wv = o;    o += D * 4;
   // ---- one lane block
   unsigned q = 0;
@@ -178,7 +191,9 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   L.lane_stride = align_up(q, 16);
   L.lanes = o;     o += L.lane_stride * G;
   L.cols = o;      o += align_up(6u * G * B * 4, 16);  // collane, colsrc, colnew, colvis, colrow (8 B each)
-  L.bars = o;      o += 2 * kStages * 8;
+  L.bars = o;
+  if constexpr (TCN > 0) o += (2 * TcCfg<H, D, TCN>::STAGES + 2 * kTcSlots + 2) * 8;  // full, empty, tfull, tempty, bready, TMEM base
+  else o += 2 * kStages * 8;
   L.misc = o;      o += 64;
   L.phase = o;     o += 128;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters
   L.xch = o; L.xbar = o;
@@ -187,6 +202,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
     L.xch = o;   o += 2u * kXchVals * (H / ((H >= 512) ? 2 : 1)) * 4;
     L.xbar = o;  o += 16;
   }
+  if (TCN > 0) o += 1024;  // slack: the kernel aligns its dynamic shared memory to 1024 bytes (swizzle atoms)
   L.total = o;
   return L;
 }
@@ -653,32 +669,192 @@ __device__ __forceinline__ void run_pass_any(const BeamParams& p, const float* r
 #undef UIS_RP
 }
 
+// ---- tensor-core weight pass (consumer warps' side; uis_beam_tc.cuh has the TMA producer and the MMA issuer) ----
+// Columns [m0, m0 + Mp), Mp <= N.  Thread <-> weight row: warp w reads TMEM lanes 32 * (w & 3) .. + 31 (the hardware
+// ties a warp to the lane quarter warp_id % 4) and takes the 8-column chunks of parity w >> 2.
+template <int H, int D, int N>
+__device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* bop, uint32_t tmem_base, const TcBars& tb,
+                                            unsigned& tcnt, const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
+                                            float* pool_hidden_cta, float* scratch_cta, int tid, int lane, int warp,
+                                            long long* ph, long long& tmark) {
+  using TC = TcCfg<H, D, N>;
+  constexpr int NT = 256;
+  const size_t lane_pool_h = (size_t)p.P * H, lane_pool_m = (size_t)p.P * D;
+  const int qd = warp & 3, hsel = warp >> 2;
+  const int r = qd * 32 + lane;
+  const uint32_t tlane = ((uint32_t)(qd * 32)) << 16;
+  auto tile_wait = [&](unsigned t) -> uint32_t {  // accumulator of tile t is complete -> its TMEM address for this warp
+    const unsigned slot = t % kTcSlots;
+    tc_mbar_wait(&tb.tfull[slot], (t / kTcSlots) & 1);
+    return tmem_base + tlane + slot * TC::NP;
+  };
+  // ---------------- B = h_src (fp16 hi / lo), then the GRU gates per 128-unit tile
+  tc_gather_b<H, N, NT>(bop, [&](int m) -> const float* {
+    return pool_hidden_cta + (size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.src[m0 + m] * H; }, Mp, p.tc_sh, tid);
+  tc_signal_b(tb.bready, lane);
+  if (tid == 0) { const long long now_ = clock64(); ph[1] += now_ - tmark; tmark = now_; }
+  for (int ut = 0; ut < TC::UT; ++ut) {
+    const int j = ut * 128 + r;
+    const float bhr = __ldg(p.bhh + j), bhz = __ldg(p.bhh + H + j), bhn = __ldg(p.bhh + 2 * H + j);
+    uint32_t ta[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) ta[g] = tile_wait(tcnt + g);
+    tc_fence_after();
+    for (int c0 = hsel * 8; c0 < Mp; c0 += 16) {
+      float gr[8], gz[8], gn[8], ho[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // per-column operands from L2 / L1, issued before the TMEM loads
+        const int m = c0 + i;
+        gr[i] = gz[i] = gn[i] = ho[i] = 0.f;
+        if (m < Mp) {
+          const float* gi = p.gi + (size_t)cc.girow[m0 + m] * 3 * H;
+          gr[i] = gi[j]; gz[i] = gi[H + j]; gn[i] = gi[2 * H + j];
+          ho[i] = pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.src[m0 + m] * H + j];
+        }
+      }
+      uint32_t a[6][8];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        tc_tmem_ld8(ta[g] + (uint32_t)c0, a[2 * g]);
+        tc_tmem_ld8(ta[g] + (uint32_t)(N + c0), a[2 * g + 1]);
+      }
+      tc_tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = c0 + i;
+        if (m < Mp) {
+          const float ar = __fmul_rn(__fadd_rn(__uint_as_float(a[0][i]), __uint_as_float(a[1][i])), p.tc_inv_hh);
+          const float az = __fmul_rn(__fadd_rn(__uint_as_float(a[2][i]), __uint_as_float(a[3][i])), p.tc_inv_hh);
+          const float an = __fmul_rn(__fadd_rn(__uint_as_float(a[4][i]), __uint_as_float(a[5][i])), p.tc_inv_hh);
+          // GRU cell, PyTorch gate order r,z,n (uisrnn.py:39-47):  h' = (h - n) * z + n
+          const float rg = sigmoid_f32(__fadd_rn(gr[i], __fadd_rn(ar, bhr)));
+          const float zg = sigmoid_f32(__fadd_rn(gz[i], __fadd_rn(az, bhz)));
+          const float ng = tanhf(__fadd_rn(gn[i], __fmul_rn(rg, __fadd_rn(an, bhn))));
+          const float hn = __fadd_rn(__fmul_rn(__fsub_rn(ho[i], ng), zg), ng);
+          pool_hidden_cta[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H + j] = hn;
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) tc_release_slot(&tb.tempty[(tcnt + g) % kTcSlots], lane);
+    tcnt += 3;
+  }
+  named_bar_sync(1, NT);  // h' of every column is in the slot pool (global memory, CTA-scope ordering)
+  if (tid == 0) { const long long now_ = clock64(); ph[2] += now_ - tmark; tmark = now_; }
+  // ---------------- B = h', a = relu(W1 h' + b1) -> scratch
+  tc_gather_b<H, N, NT>(bop, [&](int m) -> const float* {
+    return pool_hidden_cta + (size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H; }, Mp, p.tc_sh, tid);
+  tc_signal_b(tb.bready, lane);
+  for (int mt = 0; mt < TC::T2; ++mt) {
+    const int j = mt * 128 + r;
+    const float b1j = __ldg(p.b1 + j);
+    const uint32_t ta = tile_wait(tcnt);
+    tc_fence_after();
+    for (int c0 = hsel * 8; c0 < Mp; c0 += 16) {
+      uint32_t a[2][8];
+      tc_tmem_ld8(ta + (uint32_t)c0, a[0]);
+      tc_tmem_ld8(ta + (uint32_t)(N + c0), a[1]);
+      tc_tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = c0 + i;
+        if (m < Mp) {
+          const float v = __fmul_rn(__fadd_rn(__uint_as_float(a[0][i]), __uint_as_float(a[1][i])), p.tc_inv_1);
+          scratch_cta[(size_t)m * H + j] = fmaxf(__fadd_rn(v, b1j), 0.f);
+        }
+      }
+    }
+    tc_release_slot(&tb.tempty[tcnt % kTcSlots], lane);
+    tcnt += 1;
+  }
+  named_bar_sync(1, NT);
+  if (tid == 0) { const long long now_ = clock64(); ph[3] += now_ - tmark; tmark = now_; }
+  // ---------------- B = a, mean = W2 a + b2, then the running-mean update of the cluster
+  tc_gather_b<H, N, NT>(bop, [&](int m) -> const float* { return scratch_cta + (size_t)m * H; }, Mp, p.tc_sa, tid);
+  tc_signal_b(tb.bready, lane);
+  for (int mt = 0; mt < TC::T3; ++mt) {
+    const int d = mt * 128 + r;
+    const float b2d = __ldg(p.b2 + d);
+    const uint32_t ta = tile_wait(tcnt);
+    tc_fence_after();
+    for (int c0 = hsel * 8; c0 < Mp; c0 += 16) {
+      float mu_old[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = c0 + i;
+        mu_old[i] = (m < Mp) ? pool_mean_cta[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.src[m0 + m] * D + d] : 0.f;
+      }
+      uint32_t a[2][8];
+      tc_tmem_ld8(ta + (uint32_t)c0, a[0]);
+      tc_tmem_ld8(ta + (uint32_t)(N + c0), a[1]);
+      tc_tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = c0 + i;
+        if (m < Mp) {
+          const float v = __fmul_rn(__fadd_rn(__uint_as_float(a[0][i]), __uint_as_float(a[1][i])), p.tc_inv_2);
+          const float mval = __fadd_rn(v, b2d);
+          const int n = cc.vis[m0 + m];  // visits BEFORE this one (uisrnn.py:425-429)
+          // mean_set[c] = (mean_set[c] * (n - 1) + mean) / n   -- fp32, true division
+          const float mu = (n == 0) ? mval
+                                    : __fdiv_rn(__fadd_rn(__fmul_rn(mu_old[i], (float)(n - 1)), mval), (float)n);
+          pool_mean_cta[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.dst[m0 + m] * D + d] = mu;
+        }
+      }
+    }
+    tc_release_slot(&tb.tempty[tcnt % kTcSlots], lane);
+    tcnt += 1;
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 // XCL = cluster (latency) mode: the kernel is launched with thread-block clusters of 2/4/8 CTAs; the CTAs of a
 // cluster run the SAME utterances in lock step (all selection phases replicated, bit-identical), and split every
 // weight matrix by k-tiles, exchanging partial sums through distributed shared memory (xch_allreduce).
-template <int H, int D, bool DEEP, bool XCL = false>
-__global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const BeamParams p) {
+// TCN > 0 = tensor-core pass (uis_beam_tc.cuh): the three matrix products of the step run as tcgen05 MMAs over
+// TCN columns per pass; warp NW drives the tensor-map TMA, warp NW + 1 issues the MMAs and owns the TMEM allocation.
+template <int H, int D, bool DEEP, bool XCL = false, int TCN = 0>
+__global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __grid_constant__ BeamParams p) {
   using C = Cfg<H, D, XCL ? kCPCluster : kCPBeam>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
-  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr bool TC = TCN > 0;
+  static_assert(!TC || (!DEEP && !XCL && NT == 256 && C::REBALANCE), "tensor-core pass: depth 1, one CTA per lane group");
+  using TCC = TcCfg<TC ? H : 128, TC ? D : 128, TC ? TCN : 16>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // the swizzled TMA boxes / MMA operands of the tensor-core pass need 1024-byte alignment
+  unsigned char* smem = TC ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023)
+                           : smem_raw;
   const int B = p.B, Kcap = p.Kcap, G = p.G;
-  const SmemLayout L = make_layout<H, D, C::CP, XCL>(B, Kcap, G);
+  const SmemLayout L = make_layout<H, D, C::CP, XCL, TCN>(B, Kcap, G);
   float* ring = reinterpret_cast<float*>(smem + L.ring);
   float* XA = reinterpret_cast<float*>(smem + L.xa);
   float* XB = reinterpret_cast<float*>(smem + L.xb);
   float* wv = reinterpret_cast<float*>(smem + L.wv);
   int* colarr = reinterpret_cast<int*>(smem + L.cols);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* empty = full + kStages;
+  uint64_t* empty = full + (TC ? TCC::STAGES : kStages);
   volatile int* misc = reinterpret_cast<volatile int*>(smem + L.misc);
+  TcBars tb{full, empty, empty + TCC::STAGES, empty + TCC::STAGES + kTcSlots, empty + TCC::STAGES + 2 * kTcSlots};
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tb.bready + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NW);
+    if constexpr (TC) {
+      for (int s = 0; s < TCC::STAGES; ++s) {
+        mbar_init(&tb.full[s], 1);
+        mbar_init(&tb.empty[s], 1);
+      }
+      for (int s = 0; s < kTcSlots; ++s) {
+        mbar_init(&tb.tfull[s], 1);
+        mbar_init(&tb.tempty[s], NW);
+      }
+      mbar_init(tb.bready, NW);
+    } else {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], NW);
+      }
     }
     for (int i = 0; i < 16; ++i) misc[i] = 0;
     if constexpr (XCL) {
@@ -689,12 +865,44 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
     }
     fence_mbar_init();
   }
+  if constexpr (TC) {
+    if (warp == NW + 1) {  // the MMA warp owns the TMEM allocation (whole TMEM: one CTA per SM)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TCC::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+  }
   __syncthreads();
   if constexpr (XCL) cluster_sync_all();  // every peer's exchange barriers exist before anyone arrives on them
+  uint32_t tmem_base = 0;
+  if constexpr (TC) {
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
+  // end of the tensor-core kernel: every warp meets here; the allocating warp returns the TMEM columns
+  auto tc_teardown = [&]() {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NW + 1) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCC::TMEM_COLS));
+    }
+  };
 
   if (warp >= NW) {  // ---------------- producer warp (+ idle warps of its warpgroup)
     if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == NW && lane == 0) producer_loop<C, XCL>(p, ring, full, empty, misc);
+    if constexpr (TC) {
+      if (warp == NW && lane == 0)
+        tc_producer_loop<TCC, H>(&p.tc_wmap, reinterpret_cast<unsigned char*>(ring), tb, &misc[MI_DONE]);
+      else if (warp == NW + 1 && lane == 0)
+        tc_mma_loop<TCC>(reinterpret_cast<const unsigned char*>(ring), reinterpret_cast<const unsigned char*>(XA), tmem_base,
+                         tb, &misc[MI_DONE]);
+      __syncwarp();
+      tc_teardown();
+    } else {
+      if (warp == NW && lane == 0) producer_loop<C, XCL>(p, ring, full, empty, misc);
+    }
     return;
   }
   if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
@@ -712,10 +920,12 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
 
   float bh[C::RG], b1r[UPT];
 #pragma unroll
-  for (int i = 0; i < C::RG; ++i) bh[i] = p.bhh[(i / UPT) * H + tid + NT * (i % UPT)];
+  for (int i = 0; i < C::RG; ++i) bh[i] = TC ? 0.f : p.bhh[(i / UPT) * H + tid + NT * (i % UPT)];
 #pragma unroll
-  for (int u = 0; u < UPT; ++u) b1r[u] = p.b1[tid + NT * u];
-  const float b2r = (tid < D) ? p.b2[tid] : 0.f;
+  for (int u = 0; u < UPT; ++u) b1r[u] = TC ? 0.f : p.b1[tid + NT * u];
+  const float b2r = (tid < D && !TC) ? p.b2[tid] : 0.f;
+  unsigned tc_tiles = 0;  // tensor-core pass: accumulator tiles consumed so far (identical in every consumer thread)
+  float* tc_scratch_cta = TC ? p.tc_scratch + (size_t)blockIdx.x * (TC ? TCN : 1) * H : nullptr;
   if (tid < D) wv[tid] = p.wvec[tid];
   for (int g = 0; g < G; ++g) {
     if (tid < D) pool_mean_cta[g * pool_m_stride + (size_t)kInitSlot * D + tid] = p.mean0[tid];
@@ -805,7 +1015,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
     if (nact == 0) break;
 
     // ---- P0: publish this step's weight pass; per-lane candidate offsets; land x_t / gi_t
-    if (tid == 0) {
+    if (tid == 0 && !TC) {
       __threadfence_block();
       misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + 1;
     }
@@ -1034,7 +1244,11 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
         }
         if (lane == 0) ls[LS_M] = M;
       }
-    } else {
+    }
+    if (TC || warp >= G) {
+      // parents' tables -> next generation: the warps without a lane of their own (FFMA kernels: G <= 4 of 8 warps);
+      // with up to 8 lanes per CTA (tensor-core pass) every warp takes its share after its lane job
+      const int cw = TC ? NW : NW - G, cme = TC ? warp : warp - G;
       int done = 0;
       for (int g = 0; g < G; ++g) {
         volatile int* ls = LSp(g);
@@ -1046,7 +1260,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
         TabEntry* ntab = reinterpret_cast<TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)(gen ^ 1) * B * Kcap;
         const int* wins = reinterpret_cast<const int*>(lane_base(g) + L.l_wins);
         for (int r = 0; r < nwin; ++r, ++done) {
-          if (done % (NW - G) != warp - G) continue;
+          if (done % cw != cme) continue;
           const int b = wins[r];
           const int Kb = mK[b];
           for (int c = lane; c < Kb; c += 32) ntab[(size_t)r * Kcap + c] = tab[(size_t)b * Kcap + c];
@@ -1126,7 +1340,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
         colrow[f] = row0g + (lsg[LS_T] % lsg[LS_N]);
       }
     }
-    const int npass = max(1, (Mtot + C::CP - 1) / C::CP);
+    constexpr int kColsPerPass = TC ? TCN : C::CP;
+    const int npass = TC ? (Mtot + kColsPerPass - 1) / kColsPerPass : max(1, (Mtot + C::CP - 1) / C::CP);
     if (tid == 0) {
       for (int g = 0; g < G; ++g) {
         volatile int* ls = LSp(g);
@@ -1134,12 +1349,21 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       }
       st_cols += Mtot;
       st_pass += npass;
-      if (npass > 1) { __threadfence_block(); misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + (npass - 1); }
+      if (npass > 1 && !TC) { __threadfence_block(); misc[MI_PUBLISHED] = misc[MI_PUBLISHED] + (npass - 1); }
     }
     named_bar_sync(1, NT);
 
     UIS_PHASE(0);
     // ---- P5: GRU + MLP for the Mtot distinct source states, C::CP columns per weight pass
+    if constexpr (TC) {
+      for (int m0 = 0; m0 < Mtot; m0 += TCN) {
+        tc_run_pass<H, D, TC ? TCN : 16>(p, reinterpret_cast<unsigned char*>(XA), tmem_base, tb, tc_tiles, cc, m0,
+                                         min(TCN, Mtot - m0), pool_mean_cta, pool_hidden_cta, tc_scratch_cta, tid, lane,
+                                         warp, ph, tmark);
+        named_bar_sync(1, NT);
+        UIS_PHASE(4);
+      }
+    } else {
     if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
     for (int m0 = 0; m0 < Mtot; m0 += C::CP) {
       const int Mp = min(C::CP, Mtot - m0);
@@ -1167,6 +1391,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
       named_bar_sync(1, NT);
       UIS_PHASE(4);
     }
+    }  // !TC
 
     // ---- P6: advance every lane; finished utterances are back-tracked and replaced
     int fin[kMaxLanes];
@@ -1254,6 +1479,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const Bea
     atomicMax(&p.stats[4], (unsigned long long)st_maxk);
     for (int i = 0; i < 10; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }
+  if constexpr (TC) tc_teardown();
 }
 
 }  // namespace uis

@@ -20,7 +20,7 @@ UIS_ERR_CUDA = -3
 UIS_ERR_OVERFLOW = -4
 UIS_ERR_NOMEM = -5
 UIS_ERR_CAPACITY = -6
-UIS_ABI_VERSION = 2  # include/uisrnn_b200.h
+UIS_ABI_VERSION = 3  # include/uisrnn_b200.h
 
 
 class NativeError(RuntimeError):
@@ -32,7 +32,7 @@ class NativeError(RuntimeError):
 class PredictOpts(C.Structure):
   _fields_ = [('beam_size', C.c_int32), ('look_ahead', C.c_int32), ('test_iteration', C.c_int32),
               ('kcap', C.c_int32), ('n_ctas', C.c_int32), ('lanes', C.c_int32), ('cluster', C.c_int32),
-              ('reserved', C.c_int32)]
+              ('engine', C.c_int32)]
 
 
 class DebugTaps(C.Structure):
@@ -47,7 +47,8 @@ class Stats(C.Structure):
   _fields_ = [('utterances', C.c_int64), ('frames', C.c_int64), ('beam_steps', C.c_int64),
               ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
               ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32),
-              ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('cluster', C.c_int32), ('phase_cycles', C.c_int64 * 10)]
+              ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('cluster', C.c_int32), ('engine', C.c_int32),
+              ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10)]
 
   def as_dict(self):
     out = {}
@@ -214,9 +215,9 @@ class NativeModel:
     return mean0, hidden0
 
   @staticmethod
-  def _opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes=0, cluster=0):
+  def _opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes=0, cluster=0, engine=0):
     return PredictOpts(int(beam_size), int(look_ahead), int(test_iteration), int(kcap), int(n_ctas),
-                       int(lanes), int(cluster))
+                       int(lanes), int(cluster), int(engine))
 
   def _taps(self, trace_utt, n_utt, lengths, beam_size, look_ahead, test_iteration, kcap):
     """Allocates host buffers for the debug taps; returns (struct, dict of arrays)."""
@@ -242,7 +243,7 @@ class NativeModel:
     return t, bufs
 
   def predict(self, seqs, beam_size=10, look_ahead=1, test_iteration=2, kcap=0, n_ctas=0,
-              trace_utt=None, stream=0, lanes=0, cluster=0):
+              trace_utt=None, stream=0, lanes=0, cluster=0, engine=0):
     """seqs: list of C-contiguous float64 [N_u, D] arrays (host).  Returns a list of int32
     label arrays (and a dict of debug arrays when trace_utt is not None)."""
     n = len(seqs)
@@ -254,7 +255,7 @@ class NativeModel:
     in_ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in keep])
     outs = [np.empty(s.shape[0], np.int32) for s in keep]
     out_ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
-    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes, cluster)
+    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes, cluster, engine)
     taps, bufs, tp = None, None, None
     if trace_utt is not None:
       taps, bufs = self._taps(trace_utt, n, [s.shape[0] for s in keep], beam_size, look_ahead,
@@ -275,11 +276,11 @@ class NativeModel:
     return outs
 
   def predict_device(self, x_ptr, frame_offsets, labels_ptr, beam_size=10, look_ahead=1,
-                     test_iteration=2, kcap=0, n_ctas=0, stream=0, lanes=0, cluster=0):
+                     test_iteration=2, kcap=0, n_ctas=0, stream=0, lanes=0, cluster=0, engine=0):
     """Device-resident variant: x_ptr -> fp32 [rows, D], labels_ptr -> int32 [rows] (raw
     device addresses, e.g. torch.Tensor.data_ptr()).  Asynchronous on `stream`."""
     off = np.ascontiguousarray(frame_offsets, dtype=np.int64)
-    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes, cluster)
+    opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes, cluster, engine)
     rc = self._lib.uis_predict_device(self._h, C.c_void_p(x_ptr),
                                       off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1,
                                       C.byref(opts), C.c_void_p(labels_ptr), None,

@@ -25,7 +25,7 @@ from . import loss_func
 from . import utils
 
 _INITIAL_SIGMA2_VALUE = 0.1
-_DEFAULT_KCAP = 32  # clusters per hypothesis held in device tables; doubled on overflow
+_DEFAULT_KCAP = 0  # clusters per hypothesis held in device tables: 0 = the library's default (16 or 32, by kernel); grown on overflow
 
 
 class CoreRNN(nn.Module):
@@ -403,7 +403,7 @@ class UISRNN:
       except native.NativeError as err:
         if err.code != native.UIS_ERR_OVERFLOW or kcap >= 1024:
           raise
-        kcap *= 2  # a hypothesis opened more clusters than the device tables hold: grow and retry
+        kcap = 32 if kcap == 0 else kcap * 2  # a hypothesis opened more clusters than the device tables hold: grow and retry
 
   def predict_single(self, test_sequence, args):
     """Labels (list of N ints) for one test sequence [N, D] float64 (uisrnn.py:479-562)."""
@@ -494,7 +494,7 @@ class _DeviceTwin:
       except native.NativeError as err:
         if err.code != native.UIS_ERR_OVERFLOW or kcap >= 1024:
           raise
-        kcap *= 2
+        kcap = 32 if kcap == 0 else kcap * 2
 
 
 def _clone_for_device(model, device_index):
