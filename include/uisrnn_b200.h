@@ -98,6 +98,9 @@ typedef struct uis_stats {
   int64_t phase_cycles[10]; /* SM cycles summed over CTAs: [0] re-pack (P4), [1] gather, [2] GRU pass,
                                [3] W1 pass, [4] W2 pass, [5] advance/back-track, [6] frame landing
                                (P0), [7] scoring (P1), [8] ranking (P2), [9] column/slot assignment (P3) */
+  int64_t tc_cycles[4];     /* tensor-core pass, SM cycles of the MMA-issuing thread summed over CTAs: stalled on [0] a
+                               weight box not yet landed (TMA), [1] an accumulator slot not yet drained (epilogue),
+                               [2] the B operand of the next product; [3] inside passes (first operand ready -> last issue) */
 } uis_stats;
 
 int uis_version(void);

@@ -114,6 +114,7 @@ struct Params {
   int N, stages, mode;  // mode 0 = full; 1 = TMA only (no MMA); 2 = MMA only (ring filled once, no TMA in the loop)
   float sh, inv_scale;
   int write_all;
+  int commit_every, wait_every;  // mode 2 only: issue-side overhead experiments (commit to a dummy barrier / re-test a completed barrier every n MMAs)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) tc_pass_kernel(const __grid_constant__ CUtensorMap wmap, const Params p) {
@@ -129,13 +130,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pass_kernel(const __grid_const
   uint64_t* empty = bars + S;       // [S]
   uint64_t* tfull = bars + 2 * S;   // [2]
   uint64_t* tempty = tfull + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* dummy = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dummy + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    mbar_init(dummy, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {  // the MMA warp owns the TMEM allocation: 2 accumulators of N columns -> power of two >= 32
@@ -202,6 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pass_kernel(const __grid_const
               mma_f16(d_tmem, dah, dbh, idesc, (ka | kk) != 0);
               mma_f16(d_tmem, dal, dbh, idesc, 1);
               mma_f16(d_tmem, dah, dbl, idesc, 1);
+              if (p.mode == 2) {
+                const int nm = ((mt * kKA + ka) * 4 + kk + 1) * 3;  // MMAs issued so far
+                if (p.commit_every && nm % p.commit_every == 0) mma_commit(dummy);
+                if (p.wait_every && nm % p.wait_every == 0) {
+                  mbar_wait(&full[0], 0);  // phase 0 completed long ago: the cost of a successful test
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+              }
             }
           }
           if (p.mode != 2) mma_commit(&empty[s]);  // frees the ring slot when the MMAs above have read it
@@ -323,7 +334,7 @@ int main(int argc, char** argv) {
       for (int mode : {0, 1, 2}) {
         for (int grid : {1, sms}) {
           if (mode != 0 && grid == 1) continue;
-          Params p{d_hs, d_out, d_cyc, N, S, mode, sh, 1.0f / (sw * sh), 0};
+          Params p{d_hs, d_out, d_cyc, N, S, mode, sh, 1.0f / (sw * sh), 0, 0, 0};
           CK(cudaMemset(d_out, 0, (size_t)kRows * 64 * 4));
           double best = 1e30, best_issue = 1e30;
           for (int rep = 0; rep < 3; ++rep) {
@@ -353,5 +364,25 @@ int main(int argc, char** argv) {
       }
     }
   }
+  // issue-side overhead of the per-box protocol (MMA only, N = 48, one CTA per SM)
+  for (int ce : {0, 12, 6, 3})
+    for (int we : {0, 12, 6, 3}) {
+      const int N = 48, S = 3;
+      const size_t smem = 1024 + (size_t)S * kStageBytes + 2 * (size_t)N * 1024 + 256;
+      Params p{d_hs, d_out, d_cyc, N, S, 2, sh, 1.0f / (sw * sh), 0, ce, we};
+      double best = 1e30;
+      for (int rep = 0; rep < 3; ++rep) {
+        tc_pass_kernel<<<sms, kThreads, smem>>>(wmap, p);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("overhead probe: %s\n", cudaGetErrorString(e)); return 1; }
+        std::vector<long long> cyc((size_t)sms * 4);
+        CK(cudaMemcpy(cyc.data(), d_cyc, cyc.size() * 8, cudaMemcpyDeviceToHost));
+        double mx = 0;
+        for (int b = 0; b < sms; ++b) mx = std::max(mx, (double)cyc[b * 4 + 1]);
+        best = std::min(best, mx);
+      }
+      printf("mma only N=48: commit every %2d MMAs, barrier test every %2d MMAs: %6.1f cycles per MMA\n", ce, we,
+             best / (kMT * kKA * 12.0));
+    }
   return 0;
 }

@@ -28,8 +28,8 @@ def main():
   for U in sizes:
     off = np.arange(U + 1, dtype=np.int64) * n_frames
     lab = torch.empty(U * n_frames, dtype=torch.int32, device='cuda')
-    for engine in (1, 2):
-      for lanes in ([0] if engine == 1 else [0, 4, 6]):
+    for engine in [int(v) for v in os.environ.get('TC_BENCH_ENGINES', '1,2').split(',')]:
+      for lanes in ([0] if engine == 1 else [int(v) for v in os.environ.get('TC_BENCH_LANES', '0,4,6').split(',')]):
         try:
           for _ in range(2):
             model.predict_device(x_dev.data_ptr(), off, lab.data_ptr(), engine=engine, lanes=lanes)
@@ -49,7 +49,12 @@ def main():
             'cols_per_pass': round(st['gru_columns'] / max(1, st['weight_passes']), 2),
             'passes': st['weight_passes'], 'labels_equal_ffma': bool(np.array_equal(got, ref.get(U, got))),
             'mismatching_frames': int((got != ref.get(U, got)).sum()),
-            'phase_share': {n: round(c / tot, 3) for n, c in zip(PHASES, st['phase_cycles'])}}), flush=True)
+            'phase_share': {n: round(c / tot, 3) for n, c in zip(PHASES, st['phase_cycles'])},
+            'phase_us_per_cta_step': {n: round(c / 1965.0 / max(1, st['beam_steps'] / max(1, st['lanes'])), 2)
+                                      for n, c in zip(PHASES, st['phase_cycles'])},
+            'mma_issuer_us_per_pass': {n: round(c / 1965.0 / max(1, st['weight_passes']), 2) for n, c in
+                                       zip(['stall_tma', 'stall_epilogue', 'stall_operand', 'pass_issue'], st['tc_cycles'])}}),
+              flush=True)
 
 
 if __name__ == '__main__':

@@ -445,7 +445,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (int rc = m->row_off.ensure((U + 1) * sizeof(long long))) return rc;
   if (int rc = m->order.ensure(U * sizeof(int))) return rc;
   if (int rc = m->status.ensure(U * sizeof(int))) return rc;
-  if (int rc = m->queue_stats.ensure(32 * sizeof(unsigned long long))) return rc;
+  if (int rc = m->queue_stats.ensure(40 * sizeof(unsigned long long))) return rc;
   if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
   if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.G * pl.P * D * sizeof(float))) return rc;
   if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * m->depth * H * sizeof(float))) return rc;
@@ -458,7 +458,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 
   CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(m->queue_stats.p, 0, 32 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(m->queue_stats.p, 0, 40 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(m->status.p, 0xff, U * sizeof(int), st));
 
   uis::BeamParams p{};
@@ -579,9 +579,10 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 int collect(uis_model* m) {
   if (!m->stats_pending) return 0;
   CU(cudaStreamSynchronize(m->last_stream));
-  unsigned long long s[20];
+  unsigned long long s[24];
   CU(cudaMemcpy(s, m->queue_stats.as<unsigned long long>() + 8, sizeof s, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 10; ++i) m->stats.phase_cycles[i] = (int64_t)s[8 + i];
+  for (int i = 0; i < 4; ++i) m->stats.tc_cycles[i] = (int64_t)s[18 + i];
   m->stats.gru_columns = (int64_t)s[0];
   m->stats.weight_passes = (int64_t)s[1];
   m->stats.candidates = (int64_t)s[2];

@@ -195,7 +195,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   if constexpr (TCN > 0) o += (2 * TcCfg<H, D, TCN>::STAGES + 2 * kTcSlots + 2) * 8;  // full, empty, tfull, tempty, bready, TMEM base
   else o += 2 * kStages * 8;
   L.misc = o;      o += 64;
-  L.phase = o;     o += 128;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters
+  L.phase = o;     o += 128 + 32;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters; MMA issuer: 4 stall counters
   L.xch = o; L.xbar = o;
   if (XCL) {  // cluster K-split: two exchange buffers of kXchVals floats per consumer thread + 2 mbarriers
     o = align_up(o, 16);
@@ -685,7 +685,8 @@ __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* 
   const uint32_t tlane = ((uint32_t)(qd * 32)) << 16;
   auto tile_wait = [&](unsigned t) -> uint32_t {  // accumulator of tile t is complete -> its TMEM address for this warp
     const unsigned slot = t % kTcSlots;
-    tc_mbar_wait(&tb.tfull[slot], (t / kTcSlots) & 1);
+    if (p.dbg_mode & 4) tc_mbar_wait(&tb.tfull[slot], (t / kTcSlots) & 1);   // experiment: spinning wait
+    else tc_mbar_wait_parked(&tb.tfull[slot], (t / kTcSlots) & 1);
     return tmem_base + tlane + slot * TC::NP;
   };
   // ---------------- B = h_src (fp16 hi / lo), then the GRU gates per 128-unit tile
@@ -700,7 +701,7 @@ __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* 
 #pragma unroll
     for (int g = 0; g < 3; ++g) ta[g] = tile_wait(tcnt + g);
     tc_fence_after();
-    for (int c0 = hsel * 8; c0 < Mp; c0 += 16) {
+    for (int c0 = hsel * 8; c0 < ((p.dbg_mode & 2) ? 0 : Mp); c0 += 16) {
       float gr[8], gz[8], gn[8], ho[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {  // per-column operands from L2 / L1, issued before the TMEM loads
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   constexpr bool TC = TCN > 0;
   static_assert(!TC || (!DEEP && !XCL && NT == 256 && C::REBALANCE), "tensor-core pass: depth 1, one CTA per lane group");
-  using TCC = TcCfg<TC ? H : 128, TC ? D : 128, TC ? TCN : 16>;
+  using TCC = TcCfg<TC ? H : 512, TC ? D : 256, TC ? TCN : 48>;  // (a valid placeholder for the FFMA kernels)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // the swizzled TMA boxes / MMA operands of the tensor-core pass need 1024-byte alignment
   unsigned char* smem = TC ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023)
@@ -857,6 +858,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       }
     }
     for (int i = 0; i < 16; ++i) misc[i] = 0;
+    if constexpr (TC)
+      for (int i = 16; i < 20; ++i) reinterpret_cast<long long*>(smem + L.phase)[i] = 0;
     if constexpr (XCL) {
       uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.xbar);
       mbar_init(&xbar[0], cluster_nctarank() - 1);
@@ -891,13 +894,14 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
   };
 
   if (warp >= NW) {  // ---------------- producer warp (+ idle warps of its warpgroup)
-    if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if constexpr (TC) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // the unrolled MMA issue loop must not spill
+    else if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if constexpr (TC) {
-      if (warp == NW && lane == 0)
+      if (warp == NW)
         tc_producer_loop<TCC, H>(&p.tc_wmap, reinterpret_cast<unsigned char*>(ring), tb, &misc[MI_DONE]);
-      else if (warp == NW + 1 && lane == 0)
+      else if (warp == NW + 1)  // the whole warp runs the issue loop (uniform operands); one elected lane issues
         tc_mma_loop<TCC>(reinterpret_cast<const unsigned char*>(ring), reinterpret_cast<const unsigned char*>(XA), tmem_base,
-                         tb, &misc[MI_DONE]);
+                         tb, &misc[MI_DONE], reinterpret_cast<long long*>(smem + L.phase) + 16, lane);
       __syncwarp();
       tc_teardown();
     } else {
@@ -905,7 +909,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     }
     return;
   }
-  if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  if constexpr (TC) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 8 x 32 x 232 + 4 x 32 x 40 <= 64 K registers
+  else if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
 
   // ---------------- consumer threads (tid < NT); they synchronise on named barrier 1
   auto lane_base = [&](int g) -> unsigned char* { return smem + L.lanes + (size_t)g * L.lane_stride; };
@@ -949,6 +954,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     for (int i = 0; i < 16; ++i) ph[i] = 0;
     ph[10] = clock64();
   }
+  // (ph[16..19], the MMA issuer's stall counters, are zeroed by thread 0 before the first __syncthreads)
   long long& tmark = ph[10];
   long long& st_cols = ph[11]; long long& st_pass = ph[12]; long long& st_cand = ph[13]; long long& st_steps = ph[14];
   long long& st_maxk = ph[15];
@@ -1479,7 +1485,11 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     atomicMax(&p.stats[4], (unsigned long long)st_maxk);
     for (int i = 0; i < 10; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }
-  if constexpr (TC) tc_teardown();
+  if constexpr (TC) {
+    tc_teardown();  // (a __syncthreads: the issuer's counters are final)
+    if (tid == 0)
+      for (int i = 0; i < 4; ++i) atomicAdd(&p.stats[18 + i], (unsigned long long)ph[16 + i]);
+  }
 }
 
 }  // namespace uis

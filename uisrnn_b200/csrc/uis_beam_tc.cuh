@@ -41,10 +41,12 @@ struct TcCfg {
   static constexpr int NP = 2 * N;                        // B rows / accumulator columns per tile
   static constexpr int ATOM_BYTES = NP * 128;             // one k atom of the B operand
   static constexpr int BOP_BYTES = KA * ATOM_BYTES;
-  static constexpr int STAGES = (N <= 32) ? 6 : 4;        // ring depth (boxes)
+  static constexpr int STAGES = (N <= 32) ? 8 : 4;        // ring depth (boxes); divides the 2 * KA boxes of a tile
   static constexpr int TMEM_COLS = 512;
   static_assert(H % 128 == 0 && D % 128 == 0, "tensor-core pass: 128-row tiles");
   static_assert(N % 16 == 0 && NP <= 256 && kTcSlots * NP <= TMEM_COLS, "accumulator slots");
+  static_assert((2 * KA) % STAGES == 0 && STAGES % 2 == 0 && KA % 2 == 0,
+                "a tile starts at ring stage 0 and boxes go in pairs (same plane, adjacent stages and k atoms)");
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -101,6 +103,35 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a consumer warp for an accumulator tile: parked by the hardware (try_wait with a suspend-time hint) so that
+// eight waiting warps do not take issue slots from the MMA-issuing warp; bounded like tc_mbar_wait.
+__device__ __forceinline__ void tc_mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  unsigned tries = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // <= 20 us per try
+        : "memory");
+    if (ok) return;
+    if (++tries > 200000u) __trap();
+  }
+}
+
+// Same, charging the time spent stalled to a counter (shared memory; only touched when the first probe fails)
+__device__ __forceinline__ void tc_mbar_wait_timed(uint64_t* bar, uint32_t parity, long long* stall) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 8000000000ll) __trap();
+  }
+  *stall += clock64() - t0;
+}
+
 // Wait for an mbarrier phase, giving up when the consumer warps have announced the end of the kernel.
 __device__ __forceinline__ bool tc_wait_or_done(uint64_t* bar, uint32_t parity, volatile int* done_flag) {
   for (;;) {
@@ -115,6 +146,13 @@ __device__ __forceinline__ bool tc_wait_or_done(uint64_t* bar, uint32_t parity, 
     if (ok) return true;
     if (*done_flag) return false;
   }
+}
+
+// elect.sync: true in exactly one (the same) lane of a converged warp
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 struct TcBars {
@@ -133,7 +171,8 @@ __device__ __forceinline__ int tc_tile_row0(int t) {
   return 3 * H + (t - TC::T1) * 128;  // W1 rows, then W2 rows (contiguous after W_hh)
 }
 
-// ---- TMA producer (one thread): the box sequence of a pass is the same for every pass, so it free-runs ----------
+// ---- TMA producer (one warp, one elected lane issues): the box sequence of a pass is the same for every pass, so it
+// free-runs ahead of the MMAs by the depth of the ring
 template <class TC, int H>
 __device__ void tc_producer_loop(const CUtensorMap* wmap, unsigned char* ring, const TcBars& b, volatile int* done_flag) {
   unsigned it = 0;
@@ -145,8 +184,11 @@ __device__ void tc_producer_loop(const CUtensorMap* wmap, unsigned char* ring, c
         for (int ka = 0; ka < TC::KA; ++ka, ++it) {
           const unsigned s = it % TC::STAGES, ph = (it / TC::STAGES) & 1;
           if (!tc_wait_or_done(&b.empty[s], ph ^ 1, done_flag)) { run = false; break; }
-          mbar_arrive_expect_tx(&b.full[s], kTcBoxBytes);
-          tc_tma_load_2d(ring + (size_t)s * kTcBoxBytes, wmap, ka * 64, pl * TC::ROWS + row0, &b.full[s]);
+          if (tc_elect_one()) {
+            mbar_arrive_expect_tx(&b.full[s], kTcBoxBytes);
+            tc_tma_load_2d(ring + (size_t)s * kTcBoxBytes, wmap, ka * 64, pl * TC::ROWS + row0, &b.full[s]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -157,35 +199,66 @@ __device__ void tc_producer_loop(const CUtensorMap* wmap, unsigned char* ring, c
 }
 
 // ---- MMA issuer (one thread) -----------------------------------------------------------------------------------
+// The WHOLE warp runs this loop with warp-uniform values and only the tcgen05 instructions are given to one elected
+// lane: operands of UTCHMMA / UTCBAR live in uniform registers, and a loop entered by a single lane makes the compiler
+// move every operand there through a vote-and-broadcast sequence (~20 dependent instructions per MMA, measured 146
+// cycles per MMA against ~60 for the MMA itself).  Descriptors are one 64-bit constant plus the 16-byte-unit address.
+// tstat[0..3]: cycles the issuer spent stalled on (0) a ring box not yet landed, (1) an accumulator slot not yet
+// drained by the epilogue warps, (2) the B operand of the next product / the next pass; (3) cycles inside passes
 template <class TC>
 __device__ void tc_mma_loop(const unsigned char* ring, const unsigned char* bop, uint32_t tmem_base, const TcBars& b,
-                            volatile int* done_flag) {
+                            volatile int* done_flag, long long* tstat, int lane) {
   constexpr uint32_t idesc = tc_idesc_f16(TC::NP);
-  const uint32_t ring_a = smem_u32(ring), bop_a = smem_u32(bop);
-  unsigned it = 0, tc = 0, nb = 0;
+  const uint64_t desc0 = tc_desc_sw128(0);  // every field but the start address
+  const uint32_t ring16 = smem_u32(ring) >> 4, bop16 = smem_u32(bop) >> 4;
+  unsigned tc = 0, nb = 0;
   for (;;) {
     for (int t = 0; t < TC::TILES; ++t, ++tc) {
       if (t == 0 || t == TC::T1 || t == TC::T1 + TC::T2) {  // a new B operand (h_src, h', a) must be in place
+        const long long w0 = clock64();
         if (!tc_wait_or_done(b.bready, nb & 1, done_flag)) return;
+        const long long w1 = clock64();
+        if (lane == 0) { if (t == 0) tstat[3] -= w1; else tstat[2] += w1 - w0; }
         ++nb;
       }
       const unsigned slot = tc % kTcSlots;
       tc_mbar_wait(&b.tempty[slot], ((tc / kTcSlots) & 1) ^ 1);
-      tc_fence_after();
       const uint32_t d_tmem = tmem_base + slot * TC::NP;
-      for (int q = 0; q < 2 * TC::KA; ++q, ++it) {  // lo boxes, then hi boxes
-        const int ka = q % TC::KA;
-        const unsigned s = it % TC::STAGES;
-        tc_mbar_wait(&b.full[s], (it / TC::STAGES) & 1);
-        tc_fence_after();
-        const uint32_t a0 = ring_a + s * kTcBoxBytes, b0 = bop_a + (uint32_t)ka * TC::ATOM_BYTES;
+      const uint32_t tpar = (tc * (unsigned)((2 * TC::KA) / TC::STAGES)) & 1u;  // ring revolutions before this tile
+      // One tile = 2 * KA boxes (lo plane, then hi plane), a whole number of ring revolutions, so the ring stage of every
+      // box is a compile-time constant and its barrier parity is one XOR away from one.  Boxes go in pairs -- both waits, eight MMAs back to
+      // back, two commits: every instruction between two MMAs is exposed (the issuing thread cannot run ahead of the
+      // tensor pipe by more than one short MMA), measured 86 cycles per MMA in a bare loop, 130 with per-box overhead.
+#pragma unroll 1
+      for (int q = 0; q < 2 * TC::KA; q += 2) {  // (not unrolled: 16 precomputed descriptor pairs would spill)
+        constexpr int S = TC::STAGES;
+        const uint32_t s0 = (uint32_t)q % S, par = tpar ^ (((uint32_t)q / S) & 1u);  // boxes q, q + 1: stages s0, s0 + 1
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // 4 k-steps of 16 inside the 64-wide swizzle atom: +32 bytes each
-          tc_mma_f16(d_tmem, tc_desc_sw128(a0 + kk * 32), tc_desc_sw128(b0 + kk * 32), idesc, (q | kk) != 0);
-        tc_commit(&b.empty[s]);  // frees the ring box when the MMAs above have read it
+        for (int u = 0; u < 2; ++u) {
+          if (!mbar_try_wait(&b.full[s0 + u], par)) {
+            const long long w0 = clock64();
+            tc_mbar_wait(&b.full[s0 + u], par);
+            if (lane == 0) tstat[0] += clock64() - w0;
+          }
+        }
+        tc_fence_after();
+        const uint64_t adesc = desc0 + (uint64_t)(ring16 + s0 * (kTcBoxBytes >> 4));
+        const uint64_t bdesc = desc0 + (uint64_t)(bop16 + ((uint32_t)q % TC::KA) * (TC::ATOM_BYTES >> 4));
+        if (tc_elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)  // 4 k-steps of 16 inside the 64-wide swizzle atom: +32 bytes = +2 units each
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(u * (kTcBoxBytes >> 4) + 2 * kk),
+                         bdesc + (uint64_t)(u * (TC::ATOM_BYTES >> 4) + 2 * kk), idesc, (q | u | kk) != 0);
+            tc_commit(&b.empty[s0 + u]);  // frees the ring box when the MMAs above have read it
+          }
+          if (q == 2 * TC::KA - 2) tc_commit(&b.tfull[slot]);
+        }
+        __syncwarp();
       }
-      tc_commit(&b.tfull[slot]);
     }
+    if (lane == 0) tstat[3] += clock64();  // issue time of the pass (first B operand ready -> last MMA issued)
   }
 }
 
@@ -201,7 +274,7 @@ __device__ __forceinline__ void tc_gather_b(unsigned char* bop, SrcFn src, int M
   const int k = 2 * pair;
   const uint32_t koff = (uint32_t)(k >> 6) * (2u * N * 128u) + (uint32_t)(k & 7) * 2u;
   const uint32_t kchunk = (uint32_t)(k & 63) >> 3;
-  constexpr int UNR = 4;
+  constexpr int UNR = 8;
   for (int m0 = cg; m0 < Mp; m0 += CG * UNR) {
     float2 v[UNR];
 #pragma unroll

@@ -48,7 +48,7 @@ class Stats(C.Structure):
               ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
               ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32),
               ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('cluster', C.c_int32), ('engine', C.c_int32),
-              ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10)]
+              ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10), ('tc_cycles', C.c_int64 * 4)]
 
   def as_dict(self):
     out = {}
