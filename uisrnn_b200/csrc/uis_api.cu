@@ -98,7 +98,7 @@ struct uis_model {
   DevBuf logn, logtot;
   int log_cap = 0;
   // workspace
-  DevBuf x64, x32, gi, row_off, order, pool_mean, pool_hidden, bp, queue_stats, labels, status;
+  DevBuf x64, x32, gi, row_off, order, pool_mean, pool_hidden, pool_mse, bp, queue_stats, labels, status;
   DevBuf dbg_win, dbg_score, dbg_off, dbg_final_scores, dbg_final_k, dbg_best_mean, dbg_best_hidden,
       dbg_best_blocks;
   // last call
@@ -409,7 +409,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
 size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
   size_t b = 0;
   b += (size_t)pl.rows * 3 * m->H * 4;                                  // gi
-  b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->depth * m->H) * 4;    // slot pools
+  b += (size_t)pl.ctas * pl.G * pl.P * (m->D + m->depth * m->H + 1) * 4;  // slot pools (+ Gaussian term per slot)
   b += (size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B * 4;  // back-pointers
   b += (size_t)(U + 1) * 8 + (size_t)U * 8 + 256;                       // offsets, order, status
   if (pl.tcn) b += (size_t)pl.ctas * pl.tcn * m->H * 4;                 // a = relu(W1 h' + b1) between two products
@@ -449,6 +449,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (int rc = m->gi.ensure((size_t)pl.rows * 3 * H * sizeof(float))) return rc;
   if (int rc = m->pool_mean.ensure((size_t)pl.ctas * pl.G * pl.P * D * sizeof(float))) return rc;
   if (int rc = m->pool_hidden.ensure((size_t)pl.ctas * pl.G * pl.P * m->depth * H * sizeof(float))) return rc;
+  if (int rc = m->pool_mse.ensure((size_t)pl.ctas * pl.G * pl.P * sizeof(float))) return rc;
   if (int rc = m->bp.ensure((size_t)pl.ctas * pl.G * (pl.L > 1 ? (size_t)pl.maxTN + pl.maxSteps : (size_t)pl.maxN) * pl.B *
                             sizeof(unsigned)))
     return rc;
@@ -481,7 +482,7 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.U = U; p.B = pl.B; p.Kcap = pl.Kcap; p.T = pl.T; p.P = pl.P; p.maxN = pl.maxN; p.G = pl.G;
   p.L = pl.L; p.node_cap = pl.node_cap; p.leaf_cap = pl.leaf_cap; p.maxTN = pl.maxTN; p.maxSteps = pl.maxSteps;
   { const char* e = getenv("UIS_DBG_MODE"); p.dbg_mode = e ? atoi(e) : 0; }
-  p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>();
+  p.pool_mean = m->pool_mean.as<float>(); p.pool_hidden = m->pool_hidden.as<float>(); p.pool_mse = m->pool_mse.as<float>();
   p.bp = m->bp.as<unsigned>();
   p.queue = m->queue_stats.as<int>();
   p.stats = m->queue_stats.as<unsigned long long>() + 8;
@@ -723,7 +724,7 @@ int uis_model_destroy(uis_model* m) {
                     &m->hidden0, &m->wih_up_t, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
                     &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
                     &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
-                    &m->dbg_best_hidden, &m->dbg_best_blocks, &m->tc_planes, &m->tc_scratch};
+                    &m->dbg_best_hidden, &m->dbg_best_blocks, &m->tc_planes, &m->tc_scratch, &m->pool_mse};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : m->ev)
     if (e) cudaEventDestroy(e);

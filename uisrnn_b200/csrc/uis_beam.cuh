@@ -90,6 +90,7 @@ struct BeamParams {
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
   float* pool_hidden;  // [ctas*G][P][depth][H]
+  float* pool_mse;     // [ctas*G][P]  Gaussian term of the slot's mean against the lane's current frame
   unsigned* bp;        // [ctas*G][maxN][B]  (parent << 16) | cluster
   int* queue;          // [1] next position in `order`
   // outputs
@@ -144,9 +145,9 @@ struct Cfg {
 };
 
 struct SmemLayout {
-  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, phase, xch, xbar, total;
+  unsigned ring, xa, xb, wv, lanes, lane_stride, cols, bars, misc, phase, xch, xbar, slist, total;
   // offsets inside one lane block
-  unsigned l_xt, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_ls;
+  unsigned l_xt, l_tabs, l_meta, l_candoff, l_keys, l_svals, l_wins, l_wcol, l_lcol, l_used, l_scored, l_ls;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -156,7 +157,7 @@ enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRAC
        LS_NWIN, LS_ERR, LS_M, LS_COLBASE, LS_NE, LS_ROW0_LO, LS_ROW0_HI, LS_DBGROWS_LO, LS_DBGROWS_HI,
        LS_FRESH, LS_COUNT = 24 };
 // CTA scalars
-enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT };
+enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT, MI_NLIST, MI_MAXK };
 
 template <int H, int D, int kCP = kCPBeam, bool XCL = false, int TCN = 0>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
@@ -187,6 +188,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   L.l_lcol = q;    q += align_up(2u * B * 4, 16);  // lane-local column -> (source slot, new slot)
   const unsigned pw = ((unsigned)B * Kcap + B + 1 + 31) / 32;
   L.l_used = q;    q += align_up(pw * 4, 16);
+  L.l_scored = q;  q += align_up(pw * 4, 16);  // slots whose Gaussian term against the current frame is in pool_mse
   L.l_ls = q;      q += LS_COUNT * 4;
   L.lane_stride = align_up(q, 16);
   L.lanes = o;     o += L.lane_stride * G;
@@ -195,6 +197,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   if constexpr (TCN > 0) o += (2 * TcCfg<H, D, TCN>::STAGES + 2 * kTcSlots + 2) * 8;  // full, empty, tfull, tempty, bready, TMEM base
   else o += 2 * kStages * 8;
   L.misc = o;      o += 64;
+  L.slist = o;     o += 4u * 64u * G;  // (lane, slot) work list of the per-slot scoring
   L.phase = o;     o += 128 + 32;  // thread 0's statistics: 10 phase cycle counters, phase mark, 5 counters; MMA issuer: 4 stall counters
   L.xch = o; L.xbar = o;
   if (XCL) {  // cluster K-split: two exchange buffers of kXchVals floats per consumer thread + 2 mbarriers
@@ -672,11 +675,11 @@ __device__ __forceinline__ void run_pass_any(const BeamParams& p, const float* r
 // ---- tensor-core weight pass (consumer warps' side; uis_beam_tc.cuh has the TMA producer and the MMA issuer) ----
 // Columns [m0, m0 + Mp), Mp <= N.  Thread <-> weight row: warp w reads TMEM lanes 32 * (w & 3) .. + 31 (the hardware
 // ties a warp to the lane quarter warp_id % 4) and takes the 8-column chunks of parity w >> 2.
-template <int H, int D, int N>
+template <int H, int D, int N, class Idle>
 __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* bop, uint32_t tmem_base, const TcBars& tb,
                                             unsigned& tcnt, const ColCtx cc, int m0, int Mp, float* pool_mean_cta,
                                             float* pool_hidden_cta, float* scratch_cta, int tid, int lane, int warp,
-                                            long long* ph, long long& tmark) {
+                                            long long* ph, long long& tmark, Idle idle_work) {
   using TC = TcCfg<H, D, N>;
   constexpr int NT = 256;
   const size_t lane_pool_h = (size_t)p.P * H, lane_pool_m = (size_t)p.P * D;
@@ -694,6 +697,7 @@ __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* 
     return pool_hidden_cta + (size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.src[m0 + m] * H; }, Mp, p.tc_sh, tid);
   tc_signal_b(tb.bready, lane);
   if (tid == 0) { const long long now_ = clock64(); ph[1] += now_ - tmark; tmark = now_; }
+  idle_work();  // the first accumulator tiles are ~10 us away: the consumer warps use the gap (next step's Gaussian terms)
   for (int ut = 0; ut < TC::UT; ++ut) {
     const int j = ut * 128 + r;
     const float bhr = __ldg(p.bhh + j), bhz = __ldg(p.bhh + H + j), bhn = __ldg(p.bhh + 2 * H + j);
@@ -994,6 +998,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       ls[LS_ACTIVE] = 1; ls[LS_FAILED] = 0; ls[LS_TRACED] = (u == p.trace_utt); ls[LS_ERR] = 0;
       ls[LS_ROW0_LO] = (int)(row0 & 0xffffffffll); ls[LS_ROW0_HI] = (int)(row0 >> 32);
       ls[LS_DBGROWS_LO] = 0; ls[LS_DBGROWS_HI] = 0; ls[LS_FRESH] = 1;
+      for (unsigned w = 0; w < PW; ++w) reinterpret_cast<unsigned*>(lane_base(g) + L.l_scored)[w] = 0;
       int* meta = reinterpret_cast<int*>(lane_base(g) + L.l_meta);  // [gen][field][B]: K,last,tot,nl
       meta[0] = 0; meta[B] = -1; meta[2 * B] = 0; reinterpret_cast<float*>(meta)[3 * B] = 0.f;
       if (u == p.trace_utt && p.dbg_off) p.dbg_off[0] = 0;
@@ -1007,6 +1012,107 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     const long long r = row0 + (t % ls[LS_N]);
     float* xts = reinterpret_cast<float*>(lane_base(g) + L.l_xt) + (t & 1) * D;
     for (int q = tid; q < D / 4; q += NT) cp_async16(xts + q * 4, p.x + (size_t)r * D + q * 4);
+  };
+
+  // Gaussian terms per live slot.  Every consumer thread calls this (it synchronises on named barrier 1).
+  //   next == false (phase P1): slots of `used` without a bit in `scored`, against the current frame x_t;
+  //   next == true  (tensor-core engine, while the first tiles of the weight pass are multiplied): every slot the
+  //   caller marked in `scored` (the next generation's live slots, new slots excluded), against x_{t+1}.
+  // weighted_mse_loss for one row (loss_func.py:33-41): sum_d fl(fl(diff^2) * w_d), divided by the count of rows
+  // whose first squared difference is non-zero (0 -> inf / nan); stored per slot in pool_mse.
+  float* pool_mse_cta = p.pool_mse + (size_t)blockIdx.x * G * p.P;
+  unsigned* slist = reinterpret_cast<unsigned*>(smem + L.slist);
+  const int slist_cap = 64 * G;
+  auto score_live_slots = [&](bool next) {
+    for (;;) {
+      if (tid == 0) misc[MI_NLIST] = 0;
+      named_bar_sync(1, NT);
+      for (int f = tid; f < G * (int)PW; f += NT) {  // one thread per bitmap word: append its slots to the list
+        const int g = f / (int)PW, w = f % (int)PW;
+        unsigned* used = reinterpret_cast<unsigned*>(lane_base(g) + L.l_used);
+        unsigned* scored = reinterpret_cast<unsigned*>(lane_base(g) + L.l_scored);
+        unsigned bits = next ? (scored[w] & ~used[w]) : (used[w] & ~scored[w]);  // (next: `used` holds the slots already listed)
+        if (!LSp(g)[LS_ACTIVE]) bits = 0;
+        const int n = __popc(bits);
+        if (n) {
+          int pos = atomicAdd((int*)&misc[MI_NLIST], n);
+          unsigned done = 0;
+          while (bits && pos < slist_cap) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            done |= 1u << bit;
+            slist[pos++] = ((unsigned)g << 16) | (unsigned)(w * 32 + bit);
+          }
+          if (next) used[w] |= done; else scored[w] |= done;
+        }
+      }
+      named_bar_sync(1, NT);
+      const int ntot = misc[MI_NLIST], nlist = min(ntot, slist_cap);
+      // one warp per slot; each warp takes kBatch slots per trip and issues all their slot-pool loads (L2) before
+      // reducing any of them, so the L2 round trips overlap instead of serialising
+      constexpr int kBatch = 4;
+      for (int f0 = warp * kBatch; f0 < nlist; f0 += NW * kBatch) {
+        int cg[kBatch];
+        unsigned cslot[kBatch];
+        float4 m4[kBatch][(D + 127) / 128];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          const int f = f0 + q;
+          cg[q] = -1; cslot[q] = 0;
+          if (f < nlist) {
+            const unsigned ent = slist[f];
+            cg[q] = (int)(ent >> 16); cslot[q] = ent & 0xffffu;
+            const float* mu = pool_mean_cta + cg[q] * pool_m_stride + (size_t)cslot[q] * D;
+#pragma unroll
+            for (int i = 0; i < (D + 127) / 128; ++i)
+              if (lane * 4 + i * 128 < D) m4[q][i] = *reinterpret_cast<const float4*>(mu + lane * 4 + i * 128);
+          }
+        }
+        float acc[kBatch], d0sq[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          acc[q] = 0.f; d0sq[q] = 1.f;
+          const int g = cg[q] < 0 ? 0 : cg[q];
+          const float* xs = reinterpret_cast<const float*>(lane_base(g) + L.l_xt) + ((LSp(g)[LS_T] + (next ? 1 : 0)) & 1) * D;
+#pragma unroll
+          for (int i = 0; i < (D + 127) / 128; ++i) {
+            const int d = lane * 4 + i * 128;
+            if (d < D && cg[q] >= 0) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xs + d);
+              const float4 w4 = *reinterpret_cast<const float4*>(wv + d);
+              const float e0 = __fsub_rn(m4[q][i].x, x4.x), e1 = __fsub_rn(m4[q][i].y, x4.y);
+              const float e2 = __fsub_rn(m4[q][i].z, x4.z), e3 = __fsub_rn(m4[q][i].w, x4.w);
+              const float q0 = __fmul_rn(e0, e0);
+              if (d == 0) d0sq[q] = q0;
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(q0, w4.x));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e1, e1), w4.y));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e2, e2), w4.z));
+              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e3, e3), w4.w));
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // interleaved butterfly reductions
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) acc[q] = __fadd_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o));
+        }
+        // lane q finishes slot q (the tails run side by side)
+        float my_acc = acc[0], my_d0 = __shfl_sync(0xffffffffu, d0sq[0], 0);
+        int my_g = cg[0];
+        unsigned my_slot = cslot[0];
+#pragma unroll
+        for (int q = 1; q < kBatch; ++q) {
+          const float dq = __shfl_sync(0xffffffffu, d0sq[q], 0);
+          if (lane == q) { my_acc = acc[q]; my_d0 = dq; my_g = cg[q]; my_slot = cslot[q]; }
+        }
+        if (lane < kBatch && my_g >= 0) {
+          if (my_d0 == 0.f) my_acc = __fdiv_rn(my_acc, 0.f);  // zero "non-zero rows" (loss_func.py:36)
+          pool_mse_cta[(size_t)my_g * p.P + my_slot] = my_acc;
+        }
+      }
+      named_bar_sync(1, NT);  // the terms are visible to every consumer thread (CTA-scope ordering of global memory)
+      if (ntot <= slist_cap) break;  // (more slots than the list holds: another round over the unlisted ones)
+    }
   };
 
   if (tid < G) lane_fetch(tid);
@@ -1041,7 +1147,11 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     }
     for (int g = 0; g < G; ++g) {
       unsigned* used = reinterpret_cast<unsigned*>(lane_base(g) + L.l_used);
-      for (unsigned w = tid; w < PW; w += NT) used[w] = (w == 0) ? 1u : 0u;  // slot 0 = INIT, always live
+      unsigned* scored = reinterpret_cast<unsigned*>(lane_base(g) + L.l_scored);
+      for (unsigned w = tid; w < PW; w += NT) {
+        used[w] = (w == 0) ? 1u : 0u;  // slot 0 = INIT, always live
+        if (!TC) scored[w] = 0;        // (tensor-core engine: set by the pre-scoring of the previous step's pass)
+      }
     }
     cp_async_wait_all();
     named_bar_sync(1, NT);
@@ -1052,8 +1162,11 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     }
     cp_async_commit();
 
-    // ---- P1: score every candidate (b, c <= K_b) of every lane: one warp each
-    //          (uisrnn.py:409-420 existing cluster, :434-446 new cluster)
+    // ---- P1: score every candidate (b, c <= K_b) of every lane  (uisrnn.py:409-420 existing cluster, :434-446 new
+    //          cluster).  The Gaussian term depends only on (slot, x_t) -- hypotheses share most of their clusters'
+    //          states -- so it is evaluated once per LIVE SLOT (one warp each), not once per candidate; slots whose
+    //          term against x_t was already computed during the previous weight pass (tensor-core engine: the
+    //          consumer warps idle while the first tiles are multiplied) are skipped.
     {
       int ne_g[kMaxLanes], ne_tot = 0;
       for (int g = 0; g < G; ++g) { ne_g[g] = LSp(g)[LS_NE]; ne_tot += ne_g[g]; }
@@ -1086,83 +1199,26 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         reinterpret_cast<unsigned*>(lane_base(g) + L.l_svals)[e] = (unsigned)slot | ((unsigned)b << 16) | ((unsigned)c << 21);
       }
       named_bar_sync(1, NT);
-      // P1b: one warp per candidate computes the 256-d weighted MSE against the slot's running
-      // mean.  Each warp takes kBatch candidates per trip and issues all their slot-pool loads
-      // (L2) before reducing any of them, so the L2 round trips overlap instead of serialising.
-      constexpr int kBatch = 4;
-      for (int f0 = warp * kBatch; f0 < ne_tot; f0 += NW * kBatch) {
-        int cg[kBatch], ce[kBatch];
-        unsigned cinfo[kBatch];
-        float4 m4[kBatch][(D + 127) / 128];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-          const int f = f0 + q;
-          cg[q] = -1;
-          if (f < ne_tot) {
-            int g = 0, e = f;
-            while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
-            cg[q] = g; ce[q] = e;
-            cinfo[q] = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_svals)[e];
-            const float* mu = pool_mean_cta + g * pool_m_stride + (size_t)(cinfo[q] & 0xffffu) * D;
-#pragma unroll
-            for (int i = 0; i < (D + 127) / 128; ++i)
-              if (lane * 4 + i * 128 < D) m4[q][i] = *reinterpret_cast<const float4*>(mu + lane * 4 + i * 128);
-          }
-        }
-        // weighted_mse_loss for one row (loss_func.py:33-41): sum_d fl(fl(diff^2) * w_d)
-        float acc[kBatch], d0sq[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-          acc[q] = 0.f; d0sq[q] = 1.f;
-          const int g = cg[q] < 0 ? 0 : cg[q];
-          const float* xs = reinterpret_cast<const float*>(lane_base(g) + L.l_xt) + (LSp(g)[LS_T] & 1) * D;
-#pragma unroll
-          for (int i = 0; i < (D + 127) / 128; ++i) {
-            const int d = lane * 4 + i * 128;
-            if (d < D && cg[q] >= 0) {
-              const float4 x4 = *reinterpret_cast<const float4*>(xs + d);
-              const float4 w4 = *reinterpret_cast<const float4*>(wv + d);
-              const float e0 = __fsub_rn(m4[q][i].x, x4.x), e1 = __fsub_rn(m4[q][i].y, x4.y);
-              const float e2 = __fsub_rn(m4[q][i].z, x4.z), e3 = __fsub_rn(m4[q][i].w, x4.w);
-              const float q0 = __fmul_rn(e0, e0);
-              if (d == 0) d0sq[q] = q0;
-              acc[q] = __fadd_rn(acc[q], __fmul_rn(q0, w4.x));
-              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e1, e1), w4.y));
-              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e2, e2), w4.z));
-              acc[q] = __fadd_rn(acc[q], __fmul_rn(__fmul_rn(e3, e3), w4.w));
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // four interleaved butterfly reductions
-#pragma unroll
-          for (int q = 0; q < kBatch; ++q) acc[q] = __fadd_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o));
-        }
-        // lane q finishes candidate q (the four tails run side by side)
-        float my_acc = acc[0], my_d0 = __shfl_sync(0xffffffffu, d0sq[0], 0);
-        int my_g = cg[0], my_e = ce[0];
-        unsigned my_info = cinfo[0];
-#pragma unroll
-        for (int q = 1; q < kBatch; ++q) {
-          const float dq = __shfl_sync(0xffffffffu, d0sq[q], 0);
-          if (lane == q) { my_acc = acc[q]; my_d0 = dq; my_g = cg[q]; my_e = ce[q]; my_info = cinfo[q]; }
-        }
-        if (lane < kBatch && my_g >= 0) {
-          const int g = my_g, e = my_e;
-          volatile int* ls = LSp(g);
-          if (my_d0 == 0.f) my_acc = __fdiv_rn(my_acc, 0.f);  // zero "non-zero rows" (loss_func.py:36)
-          const int b = (int)((my_info >> 16) & 31u), c = (int)(my_info >> 21);
-          const float* mNl = reinterpret_cast<const float*>(lane_base(g) + L.l_meta) + ls[LS_GEN] * 4 * B + 3 * B;
-          const double pen = reinterpret_cast<const double*>(lane_base(g) + L.l_keys)[e];
-          // loss = fl32(f64(mse) - log terms); neg_likelihood accumulates in fp32 (uisrnn.py:452)
-          const float loss = __double2float_rn((double)my_acc - pen);
-          const float S = __fadd_rn(mNl[b], loss);
-          reinterpret_cast<float*>(lane_base(g) + L.l_svals)[e] = S;
-          const unsigned flat = (unsigned)(b * (ls[LS_KMAX] + 1) + c);
-          reinterpret_cast<unsigned long long*>(lane_base(g) + L.l_keys)[e] =
-              ((unsigned long long)float_order_key(S) << 32) | flat;
-          if (S < INF) atomicAdd((int*)&ls[LS_NFINITE], 1);
-        }
+      // P1s: the live slots that still lack their term against x_t
+      score_live_slots(/*against the next frame=*/false);
+      // P1c: one thread per candidate: loss = fl32(f64(mse) - log terms); neg_likelihood accumulates in fp32
+      //      (uisrnn.py:452); ranking key
+      for (int f = tid; f < ne_tot; f += NT) {
+        int g = 0, e = f;
+        while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
+        volatile int* ls = LSp(g);
+        const unsigned info = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_svals)[e];
+        const int b = (int)((info >> 16) & 31u), c = (int)(info >> 21);
+        const float mse = pool_mse_cta[(size_t)g * p.P + (info & 0xffffu)];
+        const float* mNl = reinterpret_cast<const float*>(lane_base(g) + L.l_meta) + ls[LS_GEN] * 4 * B + 3 * B;
+        const double pen = reinterpret_cast<const double*>(lane_base(g) + L.l_keys)[e];
+        const float loss = __double2float_rn((double)mse - pen);
+        const float S = __fadd_rn(mNl[b], loss);
+        reinterpret_cast<float*>(lane_base(g) + L.l_svals)[e] = S;
+        const unsigned flat = (unsigned)(b * (ls[LS_KMAX] + 1) + c);
+        reinterpret_cast<unsigned long long*>(lane_base(g) + L.l_keys)[e] =
+            ((unsigned long long)float_order_key(S) << 32) | flat;
+        if (S < INF) atomicAdd((int*)&ls[LS_NFINITE], 1);
       }
       named_bar_sync(1, NT);
       UIS_PHASE(7);
@@ -1314,6 +1370,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
           ne.pad = 0;
           ntab[(size_t)r * Kcap + c] = ne;
           nK[r] = Kb + (isnew ? 1 : 0);
+          atomicMax((int*)&misc[MI_MAXK], Kb + (isnew ? 1 : 0));
           nLast[r] = c;
           nTot[r] = mTot[b] + (moved ? 1 : 0);
           nNl[r] = S;
@@ -1362,10 +1419,51 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     UIS_PHASE(0);
     // ---- P5: GRU + MLP for the Mtot distinct source states, C::CP columns per weight pass
     if constexpr (TC) {
+      // Gaussian terms of the NEXT step, computed while the tensor pipe works on the first tiles of this pass: every
+      // slot of the next generation's tables except the ones this pass is about to write, against x_{t+1}
+      // (uisrnn.py:411-414 reads the pre-update mean; slots are immutable once written).
+      auto prescore = [&]() {
+        cp_async_wait_all();  // x_{t+1} was requested in P0
+        for (int f = tid; f < G * (int)PW; f += NT) {
+          const int g = f / (int)PW, w = f % (int)PW;
+          reinterpret_cast<unsigned*>(lane_base(g) + L.l_used)[w] = 0;    // (list marker of score_live_slots)
+          reinterpret_cast<unsigned*>(lane_base(g) + L.l_scored)[w] = 0;
+        }
+        named_bar_sync(1, NT);
+        for (int f = tid; f < G * B * Kcap; f += NT) {
+          const int g = f / (B * Kcap), r = (f / Kcap) % B, c = f % Kcap;
+          volatile int* ls = LSp(g);
+          const bool go_on = ls[LS_ACTIVE] && !ls[LS_ERR] && ls[LS_NWIN] > 0 && ls[LS_T] + 1 < ls[LS_TN];
+          if (!go_on || r >= ls[LS_NWIN]) continue;
+          const int ngen = ls[LS_GEN] ^ 1;
+          const int* nK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + ngen * 4 * B;
+          unsigned* scored = reinterpret_cast<unsigned*>(lane_base(g) + L.l_scored);
+          if (r == 0 && c == 0) atomicOr(scored, 1u);  // slot 0 = INIT (the new-cluster candidate)
+          if (c < nK[r]) {
+            const int slot = (reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)ngen * B * Kcap)[(size_t)r * Kcap + c].slot;
+            atomicOr(scored + (slot >> 5), 1u << (slot & 31));
+          }
+        }
+        named_bar_sync(1, NT);
+        for (int f = tid; f < Mtot; f += NT) {  // the slots this step's passes write: scored in P1 of the next step
+          unsigned* scored = reinterpret_cast<unsigned*>(lane_base(collane[f]) + L.l_scored);
+          atomicAnd(scored + (colnew[f] >> 5), ~(1u << (colnew[f] & 31)));
+        }
+        score_live_slots(/*against the next frame=*/true);  // (starts with a barrier)
+      };
+      auto nothing = []() {};
+      if (Mtot == 0)
+        for (int f = tid; f < G * (int)PW; f += NT)
+          reinterpret_cast<unsigned*>(lane_base(f / (int)PW) + L.l_scored)[f % (int)PW] = 0;
       for (int m0 = 0; m0 < Mtot; m0 += TCN) {
-        tc_run_pass<H, D, TC ? TCN : 16>(p, reinterpret_cast<unsigned char*>(XA), tmem_base, tb, tc_tiles, cc, m0,
-                                         min(TCN, Mtot - m0), pool_mean_cta, pool_hidden_cta, tc_scratch_cta, tid, lane,
-                                         warp, ph, tmark);
+        if (m0 == 0)
+          tc_run_pass<H, D, TC ? TCN : 16>(p, reinterpret_cast<unsigned char*>(XA), tmem_base, tb, tc_tiles, cc, m0,
+                                           min(TCN, Mtot - m0), pool_mean_cta, pool_hidden_cta, tc_scratch_cta, tid, lane,
+                                           warp, ph, tmark, prescore);
+        else
+          tc_run_pass<H, D, TC ? TCN : 16>(p, reinterpret_cast<unsigned char*>(XA), tmem_base, tb, tc_tiles, cc, m0,
+                                           min(TCN, Mtot - m0), pool_mean_cta, pool_hidden_cta, tc_scratch_cta, tid, lane,
+                                           warp, ph, tmark, nothing);
         named_bar_sync(1, NT);
         UIS_PHASE(4);
       }
@@ -1406,10 +1504,6 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       const bool act = ls[LS_ACTIVE] != 0;
       const bool failed = act && ls[LS_ERR] != 0;
       fin[g] = act && (failed || ls[LS_NWIN] == 0 || ls[LS_T] + 1 >= ls[LS_TN]);
-      if (tid == 0 && act) {
-        const int* nK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + (ls[LS_GEN] ^ 1) * 4 * B;
-        for (int r = 0; r < ls[LS_NWIN]; ++r) st_maxk = max(st_maxk, (long long)nK[r]);
-      }
     }
     for (int g = 0; g < G; ++g) {  // debug taps of finishing lanes (all threads)
       if (!fin[g]) continue;
@@ -1482,7 +1576,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     atomicAdd(&p.stats[1], (unsigned long long)st_pass);
     atomicAdd(&p.stats[2], (unsigned long long)st_cand);
     atomicAdd(&p.stats[3], (unsigned long long)st_steps);
-    atomicMax(&p.stats[4], (unsigned long long)st_maxk);
+    atomicMax(&p.stats[4], (unsigned long long)max(st_maxk, (long long)misc[MI_MAXK]));
     for (int i = 0; i < 10; ++i) atomicAdd(&p.stats[8 + i], (unsigned long long)ph[i]);
   }
   if constexpr (TC) {
