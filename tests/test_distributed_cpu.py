@@ -33,6 +33,13 @@ def _worker(rank, world, port, out_dir):
   model = uisrnn_from_weights(load_weights('model_small.npz'))
   seqs = [synth_utt(700 + i, n_frames=10 + 3 * i, dim=64, n_spk=2, noise=0.08)[0] for i in range(5)]
   merged = predict_sharded(model, seqs, inference_args(beam_size=4))
+  # lazy form: a rank holds only its own shard, the others are None / produced on demand
+  from uisrnn_b200.distributed import my_shard
+  lengths = [len(s) for s in seqs]
+  own = set(my_shard(lengths))
+  assert 0 < len(own) < len(seqs)
+  lazy = [(seqs[i] if i % 2 else (lambda i=i: seqs[i])) if i in own else None for i in range(len(seqs))]
+  assert predict_sharded(model, lazy, inference_args(beam_size=4), lengths=lengths) == merged
   np.save(os.path.join(out_dir, 'rank%d.npy' % rank), np.array(merged, dtype=object), allow_pickle=True)
   dist.destroy_process_group()
 
