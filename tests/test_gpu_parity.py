@@ -237,3 +237,44 @@ def test_depth3_untrained_matches_oracle(native):
   x = rng.standard_normal((21, D)) * 0.3
   got = model.predict([x], beam_size=6, test_iteration=2, kcap=64)[0]
   assert got.tolist() == uis_oracle.predict_single(om, x, beam_size=6, look_ahead=1, test_iteration=2)
+
+
+@pytest.mark.parametrize('H,D,depth', [(100, 40, 1), (8, 2, 2), (300, 200, 1), (129, 65, 1), (512, 100, 1), (24, 16, 3)])
+def test_any_shape_up_to_512x256_runs_zero_padded(native, H, D, depth):
+  """A model whose (hidden, dim) is not a kernel shape runs zero-padded in the next larger one (uis_model_create):
+  labels, per-step scores and the un-padded states of the best hypothesis against the oracle at the ORIGINAL shape.
+  (8, 2, depth 2) is the model of the reference's own integration test; observation_dim 16 / 100 are its other shapes."""
+  rng = np.random.default_rng(1000 * H + D)
+  u = lambda *s: (rng.uniform(-1, 1, size=s) / np.sqrt(H)).astype(np.float32)
+  w = {'depth': depth, 'w1': u(H, H), 'b1': u(H), 'w2': u(D, H), 'b2': u(D), 'h0': u(depth, 1, H),
+       'sigma2': (0.05 + 0.1 * rng.random(D)).astype(np.float32), 'transition_bias': 0.15, 'crp_alpha': 1.0}
+  for l in range(depth):
+    w['weight_ih_l%d' % l] = u(3 * H, D if l == 0 else H); w['weight_hh_l%d' % l] = u(3 * H, H)
+    w['bias_ih_l%d' % l] = u(3 * H); w['bias_hh_l%d' % l] = u(3 * H)
+  model = native.NativeModel(w)
+  om = uis_oracle.OracleModel(w)
+  mean0, hidden0 = model.constants()
+  assert mean0.shape == (D,) and hidden0.shape == (depth, H)
+  assert np.max(np.abs(mean0 - om.mean0)) < STATE_ATOL and np.max(np.abs(hidden0 - om.hidden0)) < STATE_ATOL
+  centres = rng.standard_normal((3, D))
+  xs = []
+  for n in (31, 1, 18):
+    lab = (np.arange(n) // 7) % 3
+    xs.append(centres[lab] * 0.3 + 0.05 * rng.standard_normal((n, D)))
+  got, dbg = model.predict(xs, beam_size=5, test_iteration=2, kcap=64, trace_utt=0)
+  for x, o in zip(xs, got):
+    assert o.tolist() == uis_oracle.predict_single(om, x, beam_size=5, look_ahead=1, test_iteration=2)
+  assert dbg['best_mean'].shape[1] == D and dbg['best_hidden'].shape[1:] == (depth, H)
+  la2 = model.predict(xs[:1], beam_size=3, look_ahead=2, test_iteration=1, kcap=32)[0]
+  assert la2.tolist() == uis_oracle.predict_single(om, xs[0], beam_size=3, look_ahead=2, test_iteration=1)
+
+
+def test_shapes_beyond_the_largest_kernel_fail_loudly(native):
+  H, D = 640, 256
+  z = lambda *s: np.zeros(s, np.float32)
+  w = {'depth': 1, 'weight_ih_l0': z(3 * H, D), 'weight_hh_l0': z(3 * H, H), 'bias_ih_l0': z(3 * H), 'bias_hh_l0': z(3 * H),
+       'w1': z(H, H), 'b1': z(H), 'w2': z(D, H), 'b2': z(D), 'h0': z(1, 1, H), 'sigma2': np.ones(D, np.float32),
+       'transition_bias': 0.1, 'crp_alpha': 1.0}
+  with pytest.raises(native.NativeError) as ei:
+    native.NativeModel(w)
+  assert ei.value.code == native.UIS_ERR_UNSUPPORTED

@@ -84,7 +84,8 @@ struct DevBuf {
 }  // namespace
 
 struct uis_model {
-  int device = 0, D = 0, H = 0, depth = 1, num_sms = 0;
+  int device = 0, D = 0, H = 0, depth = 1, num_sms = 0;  // D, H: the kernel shape the model runs in
+  int D_user = 0, H_user = 0;  // the caller's shape (<= D, H): smaller models are zero-padded into the next kernel shape
   double p0 = 0, alpha = 0;
   // weights, k-major
   DevBuf wih_t, whh_t, w1_t, w2_t, bih, bhh, b1, b2, wvec, mean0, hidden0;
@@ -566,9 +567,11 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
         CU(cudaMemcpy(taps->step_offsets, p.dbg_off, (size_t)(trace_steps + 1) * 8, cudaMemcpyDeviceToHost));
     }
     if (p.dbg_best_mean) {
-      CU(cudaMemcpy(taps->best_mean, p.dbg_best_mean, (size_t)pl.Kcap * D * 4, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy2D(taps->best_mean, (size_t)m->D_user * 4, p.dbg_best_mean, (size_t)D * 4, (size_t)m->D_user * 4, pl.Kcap,
+                      cudaMemcpyDeviceToHost));
       if (taps->best_hidden)
-        CU(cudaMemcpy(taps->best_hidden, p.dbg_best_hidden, (size_t)pl.Kcap * m->depth * H * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy2D(taps->best_hidden, (size_t)m->H_user * 4, p.dbg_best_hidden, (size_t)H * 4, (size_t)m->H_user * 4,
+                        (size_t)pl.Kcap * m->depth, cudaMemcpyDeviceToHost));
       if (taps->best_blocks)
         CU(cudaMemcpy(taps->best_blocks, p.dbg_best_blocks, (size_t)pl.Kcap * 4, cudaMemcpyDeviceToHost));
     }
@@ -616,6 +619,15 @@ extern "C" {
 int uis_version(void) { return UIS_ABI_VERSION; }
 const char* uis_last_error(void) { return g_err.c_str(); }
 
+static int model_create_impl(uis_model** out, int device, int D, int H, int depth, const float* w_ih, const float* w_hh,
+                             const float* b_ih, const float* b_hh, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* h0, const float* sigma2, double transition_bias,
+                             double crp_alpha, int D_user, int H_user);
+
+// Any (hidden <= 512, dim <= 256) runs in the smallest instantiated kernel shape that holds it, zero-padded: a padded
+// hidden unit has zero weights and biases (r = z = 1/2, n = 0, so it stays at its initial 0) and feeds nothing; a
+// padded observation dimension has x = mean = 0 and adds (0 - 0)^2 * w = 0 to every Gaussian term.  Adding exact
+// zeros does not change an fp32 sum, so the results are those of a kernel instantiated for the caller's shape.
 int uis_model_create(uis_model** out, int device, int D, int H, int depth, const float* w_ih, const float* w_hh,
                      const float* b_ih, const float* b_hh, const float* w1, const float* b1, const float* w2,
                      const float* b2, const float* h0, const float* sigma2, double transition_bias,
@@ -626,8 +638,68 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
     return fail(UIS_ERR_INVALID, "NULL weight pointer");
   if (depth < 1 || depth > uis::kMaxDepth)
     return fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the sm_100a kernels support 1..%d stacked GRU layers", depth, uis::kMaxDepth);
-  if (!shape_supported(H, D))
-    return fail(UIS_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for hidden=%d dim=%d", H, D);
+  if (D < 1 || H < 1) return fail(UIS_ERR_INVALID, "observation_dim and rnn_hidden_size must be >= 1");
+  if (shape_supported(H, D))
+    return model_create_impl(out, device, D, H, depth, w_ih, w_hh, b_ih, b_hh, w1, b1, w2, b2, h0, sigma2,
+                             transition_bias, crp_alpha, D, H);
+  static const int shapes[3][2] = {{128, 64}, {256, 128}, {512, 256}};
+  int Hp = 0, Dp = 0;
+  for (auto& sh : shapes)
+    if (!Hp && H <= sh[0] && D <= sh[1]) { Hp = sh[0]; Dp = sh[1]; }
+  if (!Hp)
+    return fail(UIS_ERR_UNSUPPORTED, "hidden=%d dim=%d: the sm_100a kernels hold models up to hidden=512 dim=256", H, D);
+  uis::DeviceGuard device_guard_(device);
+  CU(device_guard_.status);
+  std::vector<float> v, p_wih((size_t)3 * Hp * Dp + (size_t)(depth - 1) * 3 * Hp * Hp, 0.f), p_whh((size_t)depth * 3 * Hp * Hp, 0.f),
+      p_bih((size_t)depth * 3 * Hp, 0.f), p_bhh((size_t)depth * 3 * Hp, 0.f), p_w1((size_t)Hp * Hp, 0.f), p_b1(Hp, 0.f),
+      p_w2((size_t)Dp * Hp, 0.f), p_b2(Dp, 0.f), p_h0((size_t)depth * Hp, 0.f), p_s2(Dp, 1.f);
+  // gate blocks (r, z, n) keep their own row ranges: row g * H + j -> g * Hp + j
+  if (int r = fetch(v, w_ih, (size_t)3 * H * D + (size_t)(depth - 1) * 3 * H * H)) return r;
+  for (int g = 0; g < 3; ++g)
+    for (int j = 0; j < H; ++j)
+      std::copy(v.begin() + ((size_t)g * H + j) * D, v.begin() + ((size_t)g * H + j + 1) * D,
+                p_wih.begin() + ((size_t)g * Hp + j) * Dp);
+  for (int l = 1; l < depth; ++l)
+    for (int g = 0; g < 3; ++g)
+      for (int j = 0; j < H; ++j) {
+        const float* src = v.data() + (size_t)3 * H * D + (size_t)(l - 1) * 3 * H * H + ((size_t)g * H + j) * H;
+        std::copy(src, src + H, p_wih.begin() + (size_t)3 * Hp * Dp + (size_t)(l - 1) * 3 * Hp * Hp + ((size_t)g * Hp + j) * Hp);
+      }
+  if (int r = fetch(v, w_hh, (size_t)depth * 3 * H * H)) return r;
+  for (int l = 0; l < depth; ++l)
+    for (int g = 0; g < 3; ++g)
+      for (int j = 0; j < H; ++j) {
+        const float* src = v.data() + (size_t)l * 3 * H * H + ((size_t)g * H + j) * H;
+        std::copy(src, src + H, p_whh.begin() + (size_t)l * 3 * Hp * Hp + ((size_t)g * Hp + j) * Hp);
+      }
+  for (int which = 0; which < 2; ++which) {
+    if (int r = fetch(v, which ? b_hh : b_ih, (size_t)depth * 3 * H)) return r;
+    std::vector<float>& dst = which ? p_bhh : p_bih;
+    for (int l = 0; l < depth; ++l)
+      for (int g = 0; g < 3; ++g)
+        std::copy(v.begin() + ((size_t)l * 3 + g) * H, v.begin() + ((size_t)l * 3 + g + 1) * H,
+                  dst.begin() + ((size_t)l * 3 + g) * Hp);
+  }
+  if (int r = fetch(v, w1, (size_t)H * H)) return r;
+  for (int j = 0; j < H; ++j) std::copy(v.begin() + (size_t)j * H, v.begin() + (size_t)(j + 1) * H, p_w1.begin() + (size_t)j * Hp);
+  if (int r = fetch(v, b1, H)) return r;
+  std::copy(v.begin(), v.end(), p_b1.begin());
+  if (int r = fetch(v, w2, (size_t)D * H)) return r;
+  for (int d = 0; d < D; ++d) std::copy(v.begin() + (size_t)d * H, v.begin() + (size_t)(d + 1) * H, p_w2.begin() + (size_t)d * Hp);
+  if (int r = fetch(v, b2, D)) return r;
+  std::copy(v.begin(), v.end(), p_b2.begin());
+  if (int r = fetch(v, h0, (size_t)depth * H)) return r;
+  for (int l = 0; l < depth; ++l) std::copy(v.begin() + (size_t)l * H, v.begin() + (size_t)(l + 1) * H, p_h0.begin() + (size_t)l * Hp);
+  if (int r = fetch(v, sigma2, D)) return r;
+  std::copy(v.begin(), v.end(), p_s2.begin());
+  return model_create_impl(out, device, Dp, Hp, depth, p_wih.data(), p_whh.data(), p_bih.data(), p_bhh.data(), p_w1.data(),
+                           p_b1.data(), p_w2.data(), p_b2.data(), p_h0.data(), p_s2.data(), transition_bias, crp_alpha, D, H);
+}
+
+static int model_create_impl(uis_model** out, int device, int D, int H, int depth, const float* w_ih, const float* w_hh,
+                             const float* b_ih, const float* b_hh, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* h0, const float* sigma2, double transition_bias,
+                             double crp_alpha, int D_user, int H_user) {
   if (!(transition_bias > 0.0 && transition_bias < 1.0))
     return fail(UIS_ERR_INVALID, "transition_bias must be in (0,1), got %g", transition_bias);
   if (!(crp_alpha > 0.0)) return fail(UIS_ERR_INVALID, "crp_alpha must be > 0");
@@ -635,6 +707,7 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
   CU(device_guard_.status);
   uis_model* m = new uis_model();
   m->device = device; m->D = D; m->H = H; m->depth = depth; m->p0 = transition_bias; m->alpha = crp_alpha;
+  m->D_user = D_user; m->H_user = H_user;
   int rc = 0;
   auto body = [&]() -> int {
     cudaDeviceProp prop;
@@ -736,8 +809,10 @@ int uis_model_constants(uis_model* m, float* mean0, float* hidden0) {
   if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
   uis::DeviceGuard device_guard_(m->device);
   CU(device_guard_.status);
-  if (mean0) CU(cudaMemcpy(mean0, m->mean0.p, m->D * 4, cudaMemcpyDeviceToHost));
-  if (hidden0) CU(cudaMemcpy(hidden0, m->hidden0.p, (size_t)m->depth * m->H * 4, cudaMemcpyDeviceToHost));
+  if (mean0) CU(cudaMemcpy(mean0, m->mean0.p, m->D_user * 4, cudaMemcpyDeviceToHost));
+  if (hidden0)
+    CU(cudaMemcpy2D(hidden0, (size_t)m->H_user * 4, m->hidden0.p, (size_t)m->H * 4, (size_t)m->H_user * 4, m->depth,
+                    cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -754,7 +829,16 @@ int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_of
   if (U > 0 && pl.rows > 0 && (!x_dev || !labels_dev)) return fail(UIS_ERR_INVALID, "null device buffer");
   uis::DeviceGuard device_guard_(m->device);
   CU(device_guard_.status);
-  return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m->D != m->D_user && pl.rows > 0) {  // zero-pad the caller's rows to the kernel's row length
+    if (int rc = m->x32.ensure((size_t)pl.rows * m->D * 4)) return rc;
+    const size_t np = (size_t)pl.rows * m->D;
+    const int blocks = (int)std::min<size_t>((np + 255) / 256, (size_t)m->num_sms * 16);
+    uis::pad_rows_f32_kernel<<<blocks, 256, 0, st>>>(x_dev, m->x32.as<float>(), (size_t)pl.rows, m->D_user, m->D);
+    CU(cudaGetLastError());
+    x_dev = m->x32.as<float>();
+  }
+  return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, st);
 }
 
 int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const uis_predict_opts* opts,
@@ -772,11 +856,11 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
   uis::DeviceGuard device_guard_(m->device);
   CU(device_guard_.status);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int D = m->D;
+  const int D = m->D_user;  // the caller's rows; the device rows are padded to m->D floats
   const size_t n = (size_t)pl.rows * D;
   if (n == 0) return 0;
   if (int rc = m->x64.ensure(n * 8)) return rc;
-  if (int rc = m->x32.ensure(n * 4)) return rc;
+  if (int rc = m->x32.ensure((size_t)pl.rows * m->D * 4)) return rc;
   if (int rc = m->labels.ensure((size_t)pl.rows * 4)) return rc;
   // host -> device: one async copy per utterance straight from the caller's float64 buffers
   for (int u = 0; u < U; ++u)
@@ -785,8 +869,10 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
                          cudaMemcpyHostToDevice, st));
   {
     const int threads = 256;
-    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, (size_t)m->num_sms * 16);
-    uis::cast_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), n);
+    const size_t np = (size_t)pl.rows * m->D;
+    const int blocks = (int)std::min<size_t>((np + threads - 1) / threads, (size_t)m->num_sms * 16);
+    if (m->D == D) uis::cast_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), n);
+    else uis::cast_pad_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), (size_t)pl.rows, D, m->D);
     CU(cudaGetLastError());
   }
   if (int rc = run_device(m, m->x32.as<float>(), off.data(), U, pl, m->labels.as<int32_t>(), taps, st)) return rc;

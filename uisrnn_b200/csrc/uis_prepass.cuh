@@ -17,6 +17,26 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __rest
   for (; i < n; i += stride) out[i] = __double2float_rn(in[i]);
 }
 
+// Models smaller than the kernel shape run zero-padded (uis_model_create): rows of d values -> rows of dp >= d values.
+__global__ void cast_pad_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, size_t rows, int d, int dp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, n = rows * (size_t)dp;
+  for (; i < n; i += stride) {
+    const size_t r = i / dp;
+    const int c = (int)(i % dp);
+    out[i] = c < d ? __double2float_rn(in[r * d + c]) : 0.f;
+  }
+}
+__global__ void pad_rows_f32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, int d, int dp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, n = rows * (size_t)dp;
+  for (; i < n; i += stride) {
+    const size_t r = i / dp;
+    const int c = (int)(i % dp);
+    out[i] = c < d ? in[r * d + c] : 0.f;
+  }
+}
+
 // C[M][N] = A[M][K] * Bt[K][N] + bias[N]   (all fp32, row-major; K % 4 == 0, N % 4 == 0)
 // 128x128 CTA tile, BK = 16, 256 threads, 8x8 register micro-tile, fp32 FMA (k ascending).
 constexpr int PBM = 128, PBN = 128, PBK = 16;
