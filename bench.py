@@ -29,6 +29,7 @@ WORKLOAD = ('configs[1]: predict() synthetic 256-d d-vectors, 500-frame utteranc
             'beam_size=10, look_ahead=1, test_iteration=2')
 MODEL_FIXTURE = os.path.join(ROOT, 'tests', 'golden', 'model_toy100.npz')
 FIRST_SEED = 100000          # utterance i of the workload = synth_utt(FIRST_SEED + i)
+STRONG_UTTS = 888            # fixed list of the strong-scaling side measurement (utterances 0..887 of the job)
 MMA_FLOOR_CYCLES = 86.4      # measured: cycles per 128 x N x 16 kind::f16 MMA fed from shared memory, N <= 128
                              # (tools/tc/tc_chain_probe.cu, profiles/r2_tc_chain_probe_uniform_issue.txt)
 
@@ -215,21 +216,108 @@ def secondary_metrics(model, torch):
     tr.set_corpus(xcat, index_lists)             # as UISRNN.fit does: training set resident on the device
     sampler = utils.BatchSampler(lens, 32)
     iters, rows = 100, 0
+    fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(5 + iters):
       if i == 5:
-        tr.losses(1); t0 = time.perf_counter()
+        tr.losses(1); t0 = time.perf_counter(); fe0.record()
       chosen, li = sampler.draw()
       if i >= 5:
         rows += int(li.sum())
       tr.step_corpus(chosen)                     # asynchronous; the batch is gathered on the device
+    fe1.record()
     tr.losses(1)                                 # synchronises
     dt = time.perf_counter() - t0
-    out['config4_fit_batch32'] = {'ms_per_iteration': 1e3 * dt / iters, 'packed_rows_per_s': rows / dt,
+    out['config4_fit_batch32'] = {'ms_per_iteration': 1e3 * dt / iters, 'device_ms_per_iteration': fe0.elapsed_time(fe1) / iters,
+                                  'packed_rows_per_s': rows / dt,
                                   'includes': 'batch draw (host RNG) + device gather + forward/backward/clip/Adam kernels'}
     tr.close()
   except Exception as err:  # pylint: disable=broad-except
     out['config4_fit_batch32'] = {'error': str(err)[:200]}
   return out
+
+
+def partition_secondary(api_model, iargs, rank, world, torch, dist, barrier):
+  """Side measurements every rank takes part in: (a) STRONG scaling of the partition -- one fixed list
+  of STRONG_UTTS utterances (the first ones of the job's list) sharded over the ranks with predict_sharded, labels
+  gathered to rank 0, timed end to end; (b) data-parallel fit(): config-4 shapes, batch 32 sharded over the ranks,
+  one NCCL all-reduce of [gradients | loss statistics] per iteration.  Returns a dict on rank 0 (else None)."""
+  import random
+  from uisrnn_b200 import native, utils
+  from uisrnn_b200.distributed import my_shard, predict_sharded
+  from uisrnn_b200.synth import synth_training_set, synth_utt
+  from uisrnn_b200.uisrnn import shard_columns
+  out = {}
+  try:
+    lengths = [N_FRAMES] * STRONG_UTTS
+    own = set(my_shard(lengths))
+    held = {i: torch.from_numpy(synth_utt(FIRST_SEED + i, n_frames=N_FRAMES, dim=DIM)[0]).pin_memory() for i in own}
+    lazy = [held[i].numpy() if i in own else None for i in range(STRONG_UTTS)]
+    run = lambda: predict_sharded(api_model, lazy, iargs, lengths=lengths, root=0, as_arrays=True)
+    run(); run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+      res = run()
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device='cuda')
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = api_model._native_model().stats()  # pylint: disable=protected-access
+    digest = int(np.concatenate([np.asarray(r, dtype=np.int64) for r in res]).sum()) if rank == 0 else 0
+    out['strong_scaling_fixed_list'] = {
+        'utterances_total': STRONG_UTTS, 'utterances_per_gpu': len(own), 'e2e_ms': float(t[0]) * 1e3,
+        'frames_per_s': STRONG_UTTS * N_FRAMES / float(t[0]), 'label_checksum': digest,
+        'rank0_kernel': {'engine': st['engine'], 'lanes': st['lanes'], 'ctas': st['ctas'], 'cluster': st['cluster'],
+                         'beam_ms': st['beam_ms']},
+        'note': 'fixed total work: with fewer than 2 utterances per SM a rank leaves the 6-lane tensor-core kernel for the '
+                'one-utterance-per-CTA (or cluster) kernels, whose time is the latency of one 1000-step utterance -- the '
+                'floor of strong scaling; label_checksum must be the same at every N'}
+  except Exception as err:  # pylint: disable=broad-except
+    out['strong_scaling_fixed_list'] = {'error': str(err)[:200]}
+  try:
+    np.random.seed(0); random.seed(0)
+    seqs, ids = synth_training_set(2000, 200, n_frames=100, dim=DIM, n_spk=3)
+    xcat, ycat = utils.concatenate_training_data(seqs, ids, True, True)
+    index_lists, lens = utils.resize_indices(np.array(ycat), 10)
+    w = dict(np.load(MODEL_FIXTURE))
+    params = {'gru.weight_ih_l0': w['weight_ih_l0'], 'gru.weight_hh_l0': w['weight_hh_l0'], 'gru.bias_ih_l0': w['bias_ih_l0'],
+              'gru.bias_hh_l0': w['bias_hh_l0'], 'linear_mean1.weight': w['w1'], 'linear_mean1.bias': w['b1'],
+              'linear_mean2.weight': w['w2'], 'linear_mean2.bias': w['b2'], 'rnn_init_hidden': w['h0'].reshape(-1),
+              'sigma2': w['sigma2']}
+    hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5,
+          'grad_max_norm': 5.0, 'train_sigma2': True}
+    tr = native.NativeTrainer(params, hp, device=torch.cuda.current_device())
+    tr.set_corpus(xcat, index_lists)
+    sampler = utils.BatchSampler(lens, 32)
+    comm = torch.zeros(tr.comm_size(), dtype=torch.float32, device='cuda')
+    iters = 60
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(5 + iters):
+      if i == 5:
+        tr.losses(1); barrier(); e0.record()
+      chosen, _ = sampler.draw()                # same RNG state on every rank: the same batch
+      if world == 1:
+        tr.step_corpus(chosen)
+      else:
+        mine = shard_columns(len(chosen), rank, world)
+        tr.step_corpus(chosen[mine], mode=2)
+        tr.comm_export(comm.data_ptr())
+        dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+        tr.comm_apply(comm.data_ptr())
+    e1.record()
+    last = tr.losses(1)
+    t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device='cuda')
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out['fit_data_parallel_batch32'] = {
+        'ms_per_iteration': float(t[0]), 'columns_per_rank': -(-32 // world), 'allreduce_floats': int(tr.comm_size()),
+        'loss1_last': float(last[0, 0]),
+        'note': 'device time, max over ranks; bounded by the ~100 sequential recurrence steps of the longest sequence '
+                '(their cost barely depends on the number of live columns) plus one 6.3 MB all-reduce per iteration'}
+    tr.close()
+  except Exception as err:  # pylint: disable=broad-except
+    out['fit_data_parallel_batch32'] = {'error': str(err)[:200]}
+  return out if rank == 0 else None
 
 
 # --------------------------------------------------------------------------- CPU legs (reference / oracle)
@@ -482,8 +570,8 @@ def run_b200(args):
 
   # ---- end-to-end leg (`e2e`): the public API a user calls.  N = 1: uisrnn.UISRNN.predict(list of host float64
   #      arrays) -> list of label lists.  N > 1: uisrnn_b200.distributed.predict_sharded over the job's list (the
-  #      partition by frame count; every rank decodes its shard, the label lists are all-gathered and every rank
-  #      gets the whole ordered result).  Pinned host inputs; H2D, cast, GEMM, beam search, D2H, the Python list
+  #      partition by frame count; every rank decodes its shard, the labels are gathered to rank 0 as one int32
+  #      tensor per rank over NCCL; rank 0 holds the whole ordered result as int32 arrays).  Pinned host inputs; H2D, cast, GEMM, beam search, D2H, the Python list
   #      conversion and (N > 1) the gather of the labels are all inside the timed region.
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   api_model, iargs = build_api_model(weights, local, torch)
@@ -491,8 +579,8 @@ def run_b200(args):
   lazy = [seqs[position[i]] if i in position else None for i in range(world * U)]
 
   def step_e2e():
-    if world > 1:
-      return predict_sharded(api_model, lazy, iargs, lengths=lengths)
+    if world > 1:  # rank 0 receives the merged result (int32 arrays); the other ranks keep their own shard
+      return predict_sharded(api_model, lazy, iargs, lengths=lengths, root=0, as_arrays=True)
     return api_model.predict(seqs, iargs)
 
   for _ in range(max(1, args.warmup // 2)):
@@ -513,6 +601,9 @@ def run_b200(args):
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   dev_ms, e2e_ms = float(t[0]), float(t[1])
+  partition_extra = None
+  if not args.no_secondary:
+    partition_extra = partition_secondary(api_model, iargs, rank, world, torch, dist, barrier)
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -598,9 +689,17 @@ def run_b200(args):
                      frames * D * 4 / 1e6, frames * 3 * H * 4 / 1e6)},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': frames * D * 8 * world, 'd2h_bytes_per_step': frames * 4 * world,
               'engine': e2e_stats['engine'], 'lanes_per_cta': e2e_stats['lanes'],
-              'path': ('uisrnn_b200.distributed.predict_sharded(UISRNN, list, lengths) -> shard_by_frames -> ' if world > 1 else '') +
-                      'uisrnn.UISRNN.predict(list of pinned float64 ndarrays) -> uis_predict() C ABI: H2D, cast+GEMM+beam kernels, '
-                      'D2H int32 labels -> Python lists' + (' -> all_gather_object of the label lists' if world > 1 else '')},
+              'ms_per_step': e2e_ms / args.steps,
+              'breakdown_ms_rank0_last_step': {
+                  'uis_predict_wall': e2e_stats['host_ms'], 'h2d_copy_stream_span': e2e_stats['h2d_ms'],
+                  'cast_and_input_projection_span_overlapped_with_h2d': e2e_stats['pipeline_ms'],
+                  'beam_kernel': e2e_stats['beam_ms'], 'staging_chunks': e2e_stats['chunks'],
+                  'python_and_gather': e2e_ms / args.steps - e2e_stats['host_ms']},
+              'path': ('uisrnn_b200.distributed.predict_sharded(UISRNN, list, lengths, root=0, as_arrays=True) -> shard_by_frames -> '
+                       'uis_predict() per rank -> dist.gather of one int32 label tensor per rank -> int32 arrays on rank 0'
+                       if world > 1 else
+                       'uisrnn.UISRNN.predict(list of pinned float64 ndarrays) -> uis_predict() C ABI: chunked H2D on a copy stream || '
+                       'cast + input projection, beam kernel, one D2H copy of the int32 labels -> Python lists')},
       'gpu_launches': int(args.steps * 2),
       'clocks': clocks,
       'roofline': roof,
@@ -613,6 +712,8 @@ def run_b200(args):
   }
   if world == 1 and not args.no_secondary:
     out_line['secondary'] = secondary_metrics(model, torch)
+  if partition_extra:
+    out_line.setdefault('secondary', {}).update(partition_extra)
   if world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (bounded CPU samples, ~1 min)
     try:
       cpu, parity = cpu_baseline_and_parity({U - 1: out[U - 1]})

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UIS_ABI_VERSION 3
+#define UIS_ABI_VERSION 4
 
 typedef enum uis_status {
   UIS_OK = 0,
@@ -101,6 +101,14 @@ typedef struct uis_stats {
   int64_t tc_cycles[4];     /* tensor-core pass, SM cycles of the MMA-issuing thread summed over CTAs: stalled on [0] a
                                weight box not yet landed (TMA), [1] an accumulator slot not yet drained (epilogue),
                                [2] the B operand of the next product; [3] inside passes (first operand ready -> last issue) */
+  /* host-buffer entry point (uis_predict) only, ABI 4: */
+  float h2d_ms;             /* span of the chunked host->device copies on the copy stream                              */
+  float pipeline_ms;        /* compute stream: first cast kernel -> start of the beam kernel (casts + input projections,
+                               overlapped with the copies)                                                             */
+  float host_ms;            /* wall time inside uis_predict()                                                          */
+  int32_t chunks;           /* staging chunks the float64 rows travelled in                                            */
+  int32_t groups;           /* > 1: the list did not fit the device at once and was decoded in this many groups        */
+  int32_t reserved_;
 } uis_stats;
 
 int uis_version(void);
@@ -160,11 +168,13 @@ int uis_get_stats(uis_model* m, uis_stats* out);
 
 /* ------------------------------------------------------------------------------------------------
  * Training: one iteration of UISRNN.fit_concatenated (uisrnn/uisrnn.py:252-295) on the device.
- * Parameters are the ten tensors below, in this order, row-major fp32 (PyTorch layouts):
+ * Parameters are 4 * depth + 6 tensors, in this order, row-major fp32 (PyTorch layouts); depth 1:
  *   0 gru.weight_ih_l0 [3H,D]  1 gru.weight_hh_l0 [3H,H]  2 gru.bias_ih_l0 [3H]  3 gru.bias_hh_l0 [3H]
  *   4 linear_mean1.weight [H,H] 5 linear_mean1.bias [H]   6 linear_mean2.weight [D,H] 7 linear_mean2.bias [D]
  *   8 rnn_init_hidden [H]       9 sigma2 [D]
- * (0-7 = the "rnn parameters" group that is norm-clipped, uisrnn.py:120-133, 292.)
+ * depth > 1: the four gru tensors of layer 0, then of layer 1 (weight_ih_l1 is [3H,H]), ..., then linear_mean1/2,
+ * rnn_init_hidden [depth,H], sigma2.
+ * (all but the last two = the "rnn parameters" group that is norm-clipped, uisrnn.py:120-133, 292.)
  */
 typedef struct uis_trainer uis_trainer; /* opaque; owns parameters, gradients and Adam state */
 
@@ -174,9 +184,15 @@ typedef struct uis_train_hparams {          /* training_args, uisrnn/arguments.p
   float regularization_weight;              /* --regularization_weight                           */
   float grad_max_norm;                      /* --grad_max_norm                                   */
   int32_t train_sigma2;                     /* 1 if sigma2 is estimated (model_args.sigma2 None) */
+  /* ABI 4: stacked GRU layers (model_args, uisrnn/arguments.py:55-64; nn.GRU(num_layers, dropout), uisrnn.py:35-43) */
+  int32_t rnn_depth;                        /* --rnn_depth, 1..4 (0 = 1)                         */
+  float rnn_dropout;                        /* --rnn_dropout: applied to the output sequence of every layer but the
+                                               last, in every training iteration (train mode), when rnn_depth > 1   */
+  int64_t dropout_seed;                     /* seed of the dropout masks: keep(i) is a pure function of
+                                               (seed, iteration, layer, element) -- see uis_train.cu dropout_hash   */
 } uis_train_hparams;
 
-/* params: ten host (or device) pointers, copied.  Adam state starts at zero (a fresh optimiser per
+/* params: 4 * hp->rnn_depth + 6 host (or device) pointers, copied.  Adam state starts at zero (a fresh optimiser per
  * fit_concatenated call, uisrnn.py:235-236). */
 int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float* const* params,
                        const uis_train_hparams* hp);
@@ -184,7 +200,7 @@ int uis_trainer_destroy(uis_trainer* t);
 
 /* One iteration on one batch = what utils.pack_sequence builds (utils.py:237-246): x_host fp32
  * [L][B][D] zero-padded, time-major, row 0 all zeros; lengths[B] (incl. the zero row) sorted
- * descending with lengths[0] == L; B <= 32.  mode 0: forward + backward + clip + Adam + clamp;
+ * descending with lengths[0] == L; any B >= 1 (the recurrence runs in groups of 32 columns).  mode 0: forward + backward + clip + Adam + clamp;
  * mode 1: forward + backward only (for gradient checks); mode 2: data-parallel shard (see below).  losses_out[3] (host, may be NULL) =
  * negative log likelihood, sigma2 prior, regularisation -- the three numbers uisrnn.py:297-310 logs.
  * With losses_out == NULL the call only enqueues work on `stream` (the host batch has been staged
@@ -192,7 +208,7 @@ int uis_trainer_destroy(uis_trainer* t);
 int uis_trainer_step(uis_trainer* t, const float* x_host, const int32_t* lengths, int B, int L, int mode,
                      float* losses_out, void* stream);
 
-/* what = 0: current parameters, 1: gradients of the last step.  out: ten host pointers (NULL = skip). */
+/* what = 0: current parameters, 1: gradients of the last step.  out: 4 * depth + 6 host pointers (NULL = skip). */
 int uis_trainer_get(uis_trainer* t, int what, float* const* out);
 
 /* Losses of the last `count` (<= 4096) steps, oldest first: out[count][3] host floats.  Synchronises. */
@@ -215,7 +231,7 @@ int uis_trainer_step_corpus(uis_trainer* t, const int32_t* chosen, int B, int mo
 /*
  * Data-parallel fit() (optional): every rank runs uis_trainer_step(mode = 2) on its
  * shard of the mini-batch (forward + backward with UN-normalised gradients), exports
- *   [gradients of parameters 0-8 | per-dimension squared-residual sums | per-dimension counts | row count]
+ *   [gradients of all parameters but sigma2 | per-dimension squared-residual sums | per-dimension counts | row count]
  * (uis_trainer_comm_size() floats) into a caller-owned DEVICE buffer, all-reduces(sum) it (NCCL over
  * NVLink: one collective per iteration), and hands it back: uis_trainer_comm_apply() normalises by the
  * global row count, forms the sigma2 gradient and the three losses from the global statistics, adds the

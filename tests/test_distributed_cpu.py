@@ -40,6 +40,13 @@ def _worker(rank, world, port, out_dir):
   assert 0 < len(own) < len(seqs)
   lazy = [(seqs[i] if i % 2 else (lambda i=i: seqs[i])) if i in own else None for i in range(len(seqs))]
   assert predict_sharded(model, lazy, inference_args(beam_size=4), lengths=lengths) == merged
+  # root = 0: only rank 0 receives the merged result; the others keep their own shard in place.  as_arrays: int32 arrays
+  rooted = predict_sharded(model, lazy, inference_args(beam_size=4), lengths=lengths, root=0, as_arrays=True)
+  if rank == 0:
+    assert [r.tolist() for r in rooted] == merged and all(r.dtype == np.int32 for r in rooted)
+  else:
+    assert all((rooted[i] is not None and rooted[i].tolist() == merged[i]) if i in own else rooted[i] is None
+               for i in range(len(seqs)))
   np.save(os.path.join(out_dir, 'rank%d.npy' % rank), np.array(merged, dtype=object), allow_pickle=True)
   dist.destroy_process_group()
 

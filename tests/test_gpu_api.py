@@ -114,3 +114,20 @@ def test_fit_on_cuda_then_native_predict_matches_cpu_decoder():
   model.fit(seqs, ids, t)
   model.predict(tests[0], i)
   assert model._native[0] != before              # pylint: disable=protected-access
+
+
+def test_parallel_predict_thread_branch_on_two_devices(toy_model):
+  """with >= 2 visible GPUs `parallel_predict(num_processes=k)` shards the list by frame count and
+  decodes every shard on its own device from its own host thread (one uis_model per device).  The caller's current
+  device must be what it was, and the labels those of the reference."""
+  import torch
+  import uisrnn
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  xs, labs = toy_utterances()
+  before = torch.cuda.current_device()
+  got = uisrnn.parallel_predict(toy_model, xs, inference_args(), num_processes=torch.cuda.device_count())
+  assert got == [l.tolist() for l in labs]
+  assert torch.cuda.current_device() == before
+  # both devices did work: device 1 now holds a context with allocations made by its uis_model
+  assert torch.cuda.mem_get_info(1)[0] < torch.cuda.mem_get_info(1)[1]

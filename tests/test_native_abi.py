@@ -43,7 +43,8 @@ def test_struct_layouts_match_header(lib):
   _, native = lib
   assert ctypes.sizeof(native.PredictOpts) == 8 * 4
   assert ctypes.sizeof(native.DebugTaps) == 8 + 8 * 8
-  assert ctypes.sizeof(native.Stats) == 7 * 8 + 2 * 4 + 2 * 4 + 4 * 4 + 10 * 8 + 4 * 8  # + engine, tc_columns, tc_cycles (ABI 3)
+  assert ctypes.sizeof(native.Stats) == 7 * 8 + 2 * 4 + 2 * 4 + 4 * 4 + 10 * 8 + 4 * 8 + 6 * 4  # + host-path timings (ABI 4)
+  assert ctypes.sizeof(native.TrainHParams) == 6 * 4 + 2 * 4 + 8  # + rnn_depth, rnn_dropout, dropout_seed (ABI 4)
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu(lib):

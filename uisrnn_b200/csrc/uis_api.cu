@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -108,6 +109,16 @@ struct uis_model {
   cudaStream_t last_stream = nullptr;
   bool stats_pending = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prepass, after prepass, after beam kernel
+  // host-buffer path (uis_predict): the float64 rows travel in chunks through a small ring of staging slots on a
+  // copy stream of their own, so the H2D copy of chunk c + 1 runs under the cast + input projection of chunk c and
+  // the fp64 staging is O(chunk), not O(input); labels come back in ONE copy into pinned memory
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int kSlots = 3;
+  cudaEvent_t ev_copied[kSlots] = {nullptr, nullptr, nullptr}, ev_free[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+  cudaEvent_t ev_pipe = nullptr;  // compute stream, before the first cast
+  int32_t* labels_pin = nullptr;
+  size_t labels_pin_cap = 0;
 };
 
 namespace {
@@ -418,7 +429,7 @@ size_t workspace_bytes(const uis_model* m, const Plan& pl, int U) {
 }
 
 int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, const Plan& pl, int32_t* labels_dev,
-               const uis_debug_taps* taps, cudaStream_t st) {
+               const uis_debug_taps* taps, cudaStream_t st, bool gi_ready = false) {
   const int H = m->H, D = m->D;
   m->stats = uis_stats{};
   m->stats.utterances = U;
@@ -528,8 +539,8 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   for (auto& e : m->ev)
     if (!e) CU(cudaEventCreate(&e));
   CU(cudaEventRecord(m->ev[0], st));
-  // kernel 1: input projection GEMM
-  {
+  // kernel 1: input projection GEMM (the host-buffer path has already run it chunk by chunk, under the H2D copies)
+  if (!gi_ready) {
     dim3 grid((3 * H + uis::PBN - 1) / uis::PBN, (unsigned)((pl.rows + uis::PBM - 1) / uis::PBM));
     uis::input_proj_kernel<<<grid, 256, 0, st>>>(x_dev, m->wih_t.as<float>(), m->bih.as<float>(), m->gi.as<float>(),
                                                 (int)pl.rows, 3 * H, D);
@@ -801,6 +812,15 @@ int uis_model_destroy(uis_model* m) {
   for (DevBuf* b : bufs) b->release();
   for (auto& e : m->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : m->ev_copied)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : m->ev_free)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : m->ev_h2d)
+    if (e) cudaEventDestroy(e);
+  if (m->ev_pipe) cudaEventDestroy(m->ev_pipe);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->labels_pin) cudaFreeHost(m->labels_pin);
   delete m;
   return 0;
 }
@@ -841,10 +861,127 @@ int uis_predict_device(uis_model* m, const float* x_dev, const int64_t* frame_of
   return run_device(m, x_dev, frame_offsets, U, pl, labels_dev, taps, st);
 }
 
+}  // extern "C"
+
+namespace {
+
+int ensure_host_path(uis_model* m) {
+  if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < uis_model::kSlots; ++i) {
+    if (!m->ev_copied[i]) CU(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+    if (!m->ev_free[i]) CU(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
+  }
+  for (auto& e : m->ev_h2d)
+    if (!e) CU(cudaEventCreate(&e));
+  if (!m->ev_pipe) CU(cudaEventCreate(&m->ev_pipe));
+  for (auto& e : m->ev)
+    if (!e) CU(cudaEventCreate(&e));
+  return 0;
+}
+
+// Rows of one staging chunk of the host-buffer path (UISRNN_B200_CHUNK_MB of float64, default 32 MB: long enough
+// for full PCIe rate, short enough that the first cast starts ~0.6 ms after the call).
+size_t staging_chunk_rows(int d_user) {
+  long long mb = 32;
+  if (const char* env = std::getenv("UISRNN_B200_CHUNK_MB")) mb = std::max(0ll, std::atoll(env));  // 0 = the 256-row floor
+  return std::max<size_t>(256, (size_t)mb * (1u << 20) / ((size_t)d_user * 8));
+}
+
+// One group of utterances, host buffers in, host buffers out: chunked H2D on the copy stream || cast + input
+// projection on `st`, then the beam kernel, then one D2H copy of all labels.
+int predict_host_group(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const int64_t* off,
+                       const Plan& pl, int32_t* const* labels_out, const uis_debug_taps* taps, cudaStream_t st) {
+  const int D = m->D_user, H = m->H;  // the caller's rows; the device rows are padded to m->D floats
+  const size_t rows = (size_t)pl.rows;
+  if (rows == 0) {
+    m->stats = uis_stats{};
+    m->stats.utterances = U;
+    return 0;
+  }
+  if (int rc = ensure_host_path(m)) return rc;
+  const size_t chunk = std::min(staging_chunk_rows(D), rows);
+  const int n_chunks = (int)((rows + chunk - 1) / chunk);
+  const int slots = std::min(n_chunks, (int)uis_model::kSlots);
+  if (int rc = m->x64.ensure((size_t)slots * chunk * D * 8)) return rc;
+  if (int rc = m->x32.ensure(rows * m->D * 4)) return rc;
+  if (int rc = m->gi.ensure(rows * 3 * H * sizeof(float))) return rc;
+  if (int rc = m->labels.ensure(rows * 4)) return rc;
+  if (rows * 4 > m->labels_pin_cap) {
+    if (m->labels_pin) cudaFreeHost(m->labels_pin);
+    m->labels_pin = nullptr;
+    m->labels_pin_cap = 0;
+    const size_t want = rows * 4 + rows / 2 + 4096;
+    if (cudaMallocHost(&m->labels_pin, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(UIS_ERR_NOMEM, "cudaMallocHost(%zu) for the label staging buffer failed", want);
+    }
+    m->labels_pin_cap = want;
+  }
+  cudaStream_t cs = m->copy_stream;
+  CU(cudaEventRecord(m->ev_h2d[0], cs));
+  CU(cudaEventRecord(m->ev_pipe, st));
+  size_t r0 = 0;
+  int u = 0;
+  for (int c = 0; r0 < rows; ++c) {
+    const size_t r1 = std::min(rows, r0 + chunk);
+    const int slot = c % uis_model::kSlots;
+    double* stage = m->x64.as<double>() + (size_t)slot * chunk * D;
+    if (c >= uis_model::kSlots) CU(cudaStreamWaitEvent(cs, m->ev_free[slot], 0));  // cast of chunk c - kSlots has read the slot
+    for (size_t r = r0; r < r1;) {
+      while (u < U && (size_t)off[u + 1] <= r) ++u;  // the utterance that holds row r (empty ones are skipped)
+      const size_t take = std::min((size_t)off[u + 1], r1) - r;
+      CU(cudaMemcpyAsync(stage + (r - r0) * D, seqs[u] + (r - (size_t)off[u]) * D, take * D * 8, cudaMemcpyHostToDevice, cs));
+      r += take;
+    }
+    CU(cudaEventRecord(m->ev_copied[slot], cs));
+    CU(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
+    const size_t nr = r1 - r0, np = nr * m->D;
+    const int blocks = (int)std::min<size_t>((np + 255) / 256, (size_t)m->num_sms * 16);
+    float* x32 = m->x32.as<float>() + r0 * m->D;
+    if (m->D == D) uis::cast_f64_f32_kernel<<<blocks, 256, 0, st>>>(stage, x32, np);
+    else uis::cast_pad_f64_f32_kernel<<<blocks, 256, 0, st>>>(stage, x32, nr, D, m->D);
+    dim3 grid((3 * H + uis::PBN - 1) / uis::PBN, (unsigned)((nr + uis::PBM - 1) / uis::PBM));
+    uis::input_proj_kernel<<<grid, 256, 0, st>>>(x32, m->wih_t.as<float>(), m->bih.as<float>(),
+                                                m->gi.as<float>() + r0 * 3 * H, (int)nr, 3 * H, m->D);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(m->ev_free[slot], st));
+    r0 = r1;
+  }
+  CU(cudaEventRecord(m->ev_h2d[1], cs));
+  if (int rc = run_device(m, m->x32.as<float>(), off, U, pl, m->labels.as<int32_t>(), taps, st, /*gi_ready=*/true)) return rc;
+  m->stats.kernel_launches = 1 + 2 * (int64_t)n_chunks;
+  m->stats.chunks = n_chunks;
+  CU(cudaMemcpyAsync(m->labels_pin, m->labels.p, rows * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int q = 0; q < U; ++q)
+    if (n_frames[q] > 0) std::memcpy(labels_out[q], m->labels_pin + off[q], (size_t)n_frames[q] * 4);
+  if (int rc = collect(m)) return rc;
+  CU(cudaEventElapsedTime(&m->stats.h2d_ms, m->ev_h2d[0], m->ev_h2d[1]));
+  CU(cudaEventElapsedTime(&m->stats.pipeline_ms, m->ev_pipe, m->ev[1]));  // first cast -> beam kernel start
+  return 0;
+}
+
+void add_stats(uis_stats* a, const uis_stats& b) {
+  a->utterances += b.utterances; a->frames += b.frames; a->beam_steps += b.beam_steps; a->gru_columns += b.gru_columns;
+  a->weight_passes += b.weight_passes; a->candidates += b.candidates; a->kernel_launches += b.kernel_launches;
+  a->ctas = std::max(a->ctas, b.ctas); a->max_k = std::max(a->max_k, b.max_k);
+  a->prepass_ms += b.prepass_ms; a->beam_ms += b.beam_ms; a->h2d_ms += b.h2d_ms; a->pipeline_ms += b.pipeline_ms;
+  a->lanes = std::max(a->lanes, b.lanes); a->cluster = std::max(a->cluster, b.cluster);
+  a->engine = std::max(a->engine, b.engine); a->tc_columns = std::max(a->tc_columns, b.tc_columns);
+  for (int i = 0; i < 10; ++i) a->phase_cycles[i] += b.phase_cycles[i];
+  for (int i = 0; i < 4; ++i) a->tc_cycles[i] += b.tc_cycles[i];
+  a->chunks += b.chunks; a->groups += b.groups;
+}
+
+}  // namespace
+
+extern "C" {
+
 int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const uis_predict_opts* opts,
                 int32_t* const* labels_out, const uis_debug_taps* taps, void* stream) {
   if (!m) return fail(UIS_ERR_INVALID, "model is NULL");
   if (U < 0 || (U > 0 && (!seqs || !n_frames || !labels_out))) return fail(UIS_ERR_INVALID, "null argument");
+  const auto t_begin = std::chrono::steady_clock::now();
   std::vector<int64_t> off(U + 1, 0);
   for (int u = 0; u < U; ++u) {
     if (n_frames[u] < 0) return fail(UIS_ERR_INVALID, "negative length");
@@ -856,33 +993,45 @@ int uis_predict(uis_model* m, const double* const* seqs, const int64_t* n_frames
   uis::DeviceGuard device_guard_(m->device);
   CU(device_guard_.status);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int D = m->D_user;  // the caller's rows; the device rows are padded to m->D floats
-  const size_t n = (size_t)pl.rows * D;
-  if (n == 0) return 0;
-  if (int rc = m->x64.ensure(n * 8)) return rc;
-  if (int rc = m->x32.ensure((size_t)pl.rows * m->D * 4)) return rc;
-  if (int rc = m->labels.ensure((size_t)pl.rows * 4)) return rc;
-  // host -> device: one async copy per utterance straight from the caller's float64 buffers
-  for (int u = 0; u < U; ++u)
-    if (n_frames[u] > 0)
-      CU(cudaMemcpyAsync(m->x64.as<double>() + (size_t)off[u] * D, seqs[u], (size_t)n_frames[u] * D * 8,
-                         cudaMemcpyHostToDevice, st));
-  {
-    const int threads = 256;
-    const size_t np = (size_t)pl.rows * m->D;
-    const int blocks = (int)std::min<size_t>((np + threads - 1) / threads, (size_t)m->num_sms * 16);
-    if (m->D == D) uis::cast_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), n);
-    else uis::cast_pad_f64_f32_kernel<<<blocks, threads, 0, st>>>(m->x64.as<double>(), m->x32.as<float>(), (size_t)pl.rows, D, m->D);
-    CU(cudaGetLastError());
+  if (pl.rows == 0) return 0;
+  // Memory: the per-frame workspace (gi 12H B + fp32 rows 4D B + labels) is the part that grows with the input.
+  // A list that does not fit the device at once is decoded in groups of whole utterances, one after the other
+  // (utterances are independent, uisrnn.py:587-589); UISRNN_B200_MAX_ROWS forces a limit (tests).
+  const size_t per_row = (size_t)3 * m->H * 4 + (size_t)m->D * 4 + 4;
+  size_t max_rows = 0;
+  if (const char* env = std::getenv("UISRNN_B200_MAX_ROWS")) max_rows = (size_t)std::max(1ll, std::atoll(env));
+  if (!max_rows) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t held = m->gi.cap + m->x32.cap + m->labels.cap + m->x64.cap;  // re-used by this call
+    const size_t fixed = workspace_bytes(m, pl, U) - (size_t)pl.rows * 3 * m->H * 4 +
+                         (size_t)uis_model::kSlots * staging_chunk_rows(m->D_user) * m->D_user * 8;
+    const double budget = 0.9 * (double)(free_b + held) - (double)fixed;
+    max_rows = budget > (double)per_row ? (size_t)(budget / (double)per_row) : 1;
   }
-  if (int rc = run_device(m, m->x32.as<float>(), off.data(), U, pl, m->labels.as<int32_t>(), taps, st)) return rc;
-  m->stats.kernel_launches += 1;
-  for (int u = 0; u < U; ++u)
-    if (n_frames[u] > 0)
-      CU(cudaMemcpyAsync(labels_out[u], m->labels.as<int32_t>() + off[u], (size_t)n_frames[u] * 4,
-                         cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  return collect(m);
+  if ((size_t)pl.rows <= max_rows || taps || U <= 1) {
+    if (int rc = predict_host_group(m, seqs, n_frames, U, off.data(), pl, labels_out, taps, st)) return rc;
+    m->stats.groups = 1;
+  } else {
+    uis_stats total{};
+    int u0 = 0;
+    while (u0 < U) {
+      int u1 = u0 + 1;
+      while (u1 < U && (size_t)(off[u1 + 1] - off[u0]) <= max_rows) ++u1;
+      std::vector<int64_t> goff(u1 - u0 + 1);
+      for (int q = u0; q <= u1; ++q) goff[q - u0] = off[q] - off[u0];
+      Plan gp;
+      if (int rc = make_plan(m, goff.data(), u1 - u0, opts, &gp, false)) return rc;
+      if (int rc = predict_host_group(m, seqs + u0, n_frames + u0, u1 - u0, goff.data(), gp, labels_out + u0, nullptr, st))
+        return rc;
+      m->stats.groups = 1;
+      add_stats(&total, m->stats);
+      u0 = u1;
+    }
+    m->stats = total;
+  }
+  m->stats.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  return 0;
 }
 
 int uis_get_stats(uis_model* m, uis_stats* out) {

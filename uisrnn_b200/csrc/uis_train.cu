@@ -10,6 +10,7 @@
 // t the first batch_t = #{len_b > t} sequences are live, as in a PackedSequence.
 // All arithmetic fp32.  The derivation of the backward pass is checked against torch autograd in
 // tools/fit_manual_check.py (CPU) and tests/test_gpu_fit.py (device).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -248,7 +249,9 @@ __global__ void gru_gate_fwd_kernel(const float* __restrict__ gh, const float* _
 // needs stay in its shared memory (24 KB) for all L steps -- and the CTAs exchange h_t (forward) / dGh_t
 // (backward) through L2 with one grid-wide barrier per step.  H % 128 == 0, H / 4 CTAs (128 at H = 512).
 constexpr int kUPC = 4;
-struct SeqParams { int length[32]; int L, B, H; };
+// One launch covers a group of <= 32 batch columns [b0, b0 + B) of a batch that is `stride` columns wide (the
+// pointers handed to the kernels are already offset to column b0); wider batches run group after group.
+struct SeqParams { int length[32]; int L, B, H, stride, spin_barrier; };
 
 __device__ __forceinline__ int seq_rows_alive(const SeqParams& sp, int t) {
   int nb = 0;
@@ -256,9 +259,14 @@ __device__ __forceinline__ int seq_rows_alive(const SeqParams& sp, int t) {
   return nb;
 }
 
-// All CTAs arrive; returns when `target` arrivals are visible.  Bounded spin: a lost CTA sets *err instead of
-// hanging the device (the launch is cooperative, so co-residency is guaranteed and this never fires).
-__device__ __forceinline__ void seq_grid_sync(unsigned* bar, unsigned target, int* err) {
+// Grid-wide barrier of the persistent recurrence kernels (cooperative launch: all CTAs are co-resident).  Default:
+// cooperative_groups grid.sync().  UISRNN_B200_TRAIN_BARRIER=spin selects the earlier hand-rolled arrival counter
+// (kept for A/B timing; bounded spin, a lost CTA sets *err instead of hanging the device).
+__device__ __forceinline__ void seq_grid_sync(const SeqParams& sp, unsigned* bar, unsigned target, int* err) {
+  if (!sp.spin_barrier) {
+    cooperative_groups::this_grid().sync();
+    return;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restric
                                                           float* __restrict__ n_o, float* __restrict__ hn_o,
                                                           SeqParams sp, unsigned* bar, int* err) {
   extern __shared__ float4 seq_smem[];
-  const int H = sp.H, B = sp.B, S = H + 4, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int H = sp.H, B = sp.stride, S = H + 4, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   float* sW = reinterpret_cast<float*>(seq_smem);  // [3 * kUPC][H]: row g * kUPC + u = W_hh[g * H + j0 + u][:]
   float* sh = sW + 3 * kUPC * H;                   // [32][H + 4]
   float* sred = sh + 32 * S;                       // [8][3 * kUPC][32]
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restric
       }
     }
     fetch_gi(t + 1);
-    seq_grid_sync(bar, (unsigned)(t + 1) * gridDim.x, err);
+    seq_grid_sync(sp, bar, (unsigned)(t + 1) * gridDim.x, err);
   }
 }
 
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restric
                                                           float* dgh, float* __restrict__ carry_out, SeqParams sp,
                                                           unsigned* bar, int* err) {
   extern __shared__ float4 seq_smem[];
-  const int H = sp.H, B = sp.B, H3 = 3 * H, CH = H3 / 4, S = CH + 4, rpw = CH / 8;
+  const int H = sp.H, B = sp.stride, H3 = 3 * H, CH = H3 / 4, S = CH + 4, rpw = CH / 8;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, j0 = blockIdx.x * kUPC;
   float4* sWT = seq_smem;                                 // [3H]: W_hh[row][j0 .. j0 + 3]
   float* sg = reinterpret_cast<float*>(sWT + H3);         // [2][32][CH + 4]
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restric
       gh[aj] = dar; gh[H + aj] = daz; gh[2 * H + aj] = dan * r;
       scarry[tid] = dh * z;
     }
-    seq_grid_sync(bar, ++epoch * gridDim.x, err);
+    seq_grid_sync(sp, bar, ++epoch * gridDim.x, err);
     fetch_a(t - 1);
     // dGh_t (written by every CTA before the barrier) streams through two staging buffers: L2 -> smem copies
     // (cp.async.cg: L2 only, never a stale L1 line) of chunk c + 1 run under the product with chunk c
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(256) gru_seq_bwd_kernel(const float* __restric
   }
   if (tid < 32 * kUPC) {
     const int b = tid >> 2, u = tid & 3;
-    if (b < B) carry_out[(size_t)b * H + j0 + u] = scarry[tid];
+    if (b < sp.B) carry_out[(size_t)b * H + j0 + u] = scarry[tid];
   }
 }
 
@@ -633,14 +641,35 @@ __global__ void scale_by_inv_kernel(float* __restrict__ g, const float* __restri
 // fp32 rows; a mini-batch is a gather.  x[t][b][:] = 0 for t = 0 (the prepended zero frame, utils.py:243) and
 // for t >= length_b (padding), else rows[index[begin_b + t - 1]][:].
 struct GatherCols { long long begin[32]; int length[32]; };
+// columns [b0, b0 + nbg) of a batch B columns wide; grid = L * nbg
 __global__ void gather_batch_kernel(const float* __restrict__ rows, const int* __restrict__ index, GatherCols cols,
-                                    float* __restrict__ x, int L, int B, int D) {
-  const int tb = blockIdx.x;  // t * B + b
-  const int tt = tb / B, b = tb % B;
-  float* dst = x + (size_t)tb * D;
-  const bool live = tt >= 1 && tt < cols.length[b];
-  const float* src = live ? rows + (size_t)index[cols.begin[b] + tt - 1] * D : nullptr;
+                                    float* __restrict__ x, int nbg, int b0, int B, int D) {
+  const int tt = blockIdx.x / nbg, bl = blockIdx.x % nbg;
+  float* dst = x + ((size_t)tt * B + b0 + bl) * D;
+  const bool live = tt >= 1 && tt < cols.length[bl];
+  const float* src = live ? rows + (size_t)index[cols.begin[bl] + tt - 1] * D : nullptr;
   for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = live ? src[i] : 0.f;
+}
+
+// Inter-layer dropout of the stacked GRU in train mode (nn.GRU(dropout=p), uisrnn.py:39-41): element i of the output
+// of layer `layer` in iteration `iter` is kept with probability 1 - p and scaled by 1 / (1 - p).  The keep decision
+// is a pure function of (seed, iter, layer, i) -- a 32-bit integer hash, restated in tests/test_gpu_fit.py -- so the
+// backward pass regenerates the mask instead of storing it.  (PyTorch draws its masks from the device generator /
+// cuDNN dropout state; the streams differ, the distribution is the same.)
+__host__ __device__ __forceinline__ unsigned dropout_hash(unsigned seed, unsigned iter, unsigned layer, unsigned i) {
+  unsigned h = seed ^ (iter * 0x9E3779B1u) ^ (layer * 0x85EBCA77u) ^ (i * 0xC2B2AE3Du);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+// out[i] = in[i] * keep(i) / (1 - p); in == out is fine
+__global__ void dropout_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, unsigned seed,
+                               unsigned iter, unsigned layer, float p, float inv_keep) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float u = (float)(dropout_hash(seed, iter, layer, (unsigned)i) >> 8) * (1.0f / 16777216.0f);
+    out[i] = u >= p ? in[i] * inv_keep : 0.f;
+  }
 }
 __global__ void set_scalar_kernel(float* p, float v) { *p = v; }
 __global__ void cast_rows_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -690,16 +719,33 @@ int gemm(cudaStream_t st, const SplitCtx& sc, const float* A, const float* B, co
 
 }  // namespace uis
 
+constexpr int kMaxTrainDepth = 4;
+constexpr int kMaxSegs = 4 * kMaxTrainDepth + 6;
+
 struct uis_trainer {
-  int device = 0, D = 0, H = 0;
+  int device = 0, D = 0, H = 0, depth = 1;
   uis_train_hparams hp{};
-  int seg_off_h[11];
+  // parameter segments: [W_ih_l, W_hh_l, b_ih_l, b_hh_l] per layer, W1, b1, W2, b2, h0 [depth][H], sigma2
+  int n_seg = 10, n_rnn_seg = 8;
+  int seg_off_h[kMaxSegs + 1];
   int total = 0, rnn_end = 0, sigma_begin = 0;
+  int seg_wih(int l) const { return 4 * l; }
+  int seg_whh(int l) const { return 4 * l + 1; }
+  int seg_bih(int l) const { return 4 * l + 2; }
+  int seg_bhh(int l) const { return 4 * l + 3; }
+  int seg_w1() const { return 4 * depth; }
+  int seg_b1() const { return 4 * depth + 1; }
+  int seg_w2() const { return 4 * depth + 2; }
+  int seg_b2() const { return 4 * depth + 3; }
+  int seg_h0() const { return 4 * depth + 4; }
+  int seg_sigma2() const { return 4 * depth + 5; }
   long long step = 0, calls = 0;
   uis::DBuf params, grads, m, v, segbuf;  // segbuf: seg_off (as int bits) is separate below
   int* seg_off_d = nullptr;
-  float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 16][g_sumsq 16]
-  uis::DBuf x, gi, hs, r, z, n, hn, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial, skpart;
+  float* small = nullptr;  // [sum_sq_d D][cnt_d D][nz 1][scalars 4][p_sumsq 32][g_sumsq 32]
+  // gi, hs, r, z, n, hn: one slab per layer (the backward pass needs every layer's activations); xin: the (dropped)
+  // input sequence of layers >= 1
+  uis::DBuf x, gi, hs, r, z, n, hn, xin, a1, mu, diff, dmu, dz1, dout, dgi, dgh, carry, whh_t, ghbuf, partial, skpart;
   unsigned* tickets = nullptr;
   uis::SplitCtx sc;
   uis::DBuf gemm_partial, loss_hist;
@@ -713,15 +759,12 @@ struct uis_trainer {
   // corpus path: training rows (fp32) + flat gather indices + per-sub-sequence offsets (host copy)
   unsigned* seq_bar = nullptr;  // [2] arrival counters of the persistent recurrence kernels; [2] = error flag
   int seq_mode = -1;            // -1 unknown, 0 per-step launches, 1 persistent cooperative kernels
+  int spin_barrier = 0;
   uis::DBuf corpus;
   int* corpus_index = nullptr;
   long long corpus_rows = 0;
   std::vector<long long> sub_off;
 };
-
-namespace {
-enum { SEG_WIH = 0, SEG_WHH, SEG_BIH, SEG_BHH, SEG_W1, SEG_B1, SEG_W2, SEG_B2, SEG_H0, SEG_SIGMA2, SEG_COUNT };
-}
 
 namespace {
 
@@ -733,23 +776,24 @@ int finish_step(uis_trainer* t, cudaStream_t st, int mode, float* losses_out) {
   float* G = t->grads.p;
   const int* so = t->seg_off_h;
   float* nz = t->small + 2 * D;
-  float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 16;
-  seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(P, t->seg_off_d, t->partial.p);
-  seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, p_sumsq);
+  float* scalars = nz + 1; float* p_sumsq = scalars + 4; float* g_sumsq = p_sumsq + 32;
+  const int nrs = t->n_rnn_seg;  // the tensors of rnn_model.parameters(): regularised one by one, clipped as a group
+  seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, nrs), 256, 0, st>>>(P, t->seg_off_d, t->partial.p);
+  seg_sumsq_final_kernel<<<nrs, kSumsqBlocks, 0, st>>>(t->partial.p, p_sumsq);
   {
     int maxseg = 0;
-    for (int s = 0; s < 8; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
-    dim3 grid((maxseg + 255) / 256, 8);
-    reg_grad_kernel<<<grid, 256, 0, st>>>(P, G, t->seg_off_d, p_sumsq, t->hp.regularization_weight, 8, scalars);
+    for (int s = 0; s < nrs; ++s) maxseg = std::max(maxseg, so[s + 1] - so[s]);
+    dim3 grid((maxseg + 255) / 256, nrs);
+    reg_grad_kernel<<<grid, 256, 0, st>>>(P, G, t->seg_off_d, p_sumsq, t->hp.regularization_weight, nrs, scalars);
   }
   CUT(cudaGetLastError());
   if (mode == 0) {
-    seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, 8), 256, 0, st>>>(G, t->seg_off_d, t->partial.p);
-    seg_sumsq_final_kernel<<<8, kSumsqBlocks, 0, st>>>(t->partial.p, g_sumsq);
+    seg_sumsq_partial_kernel<<<dim3(kSumsqBlocks, nrs), 256, 0, st>>>(G, t->seg_off_d, t->partial.p);
+    seg_sumsq_final_kernel<<<nrs, kSumsqBlocks, 0, st>>>(t->partial.p, g_sumsq);
     t->step += 1;
     // torch.optim.Adam (defaults): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles
     const double bc1 = 1.0 - std::pow(0.9, (double)t->step), bc2 = 1.0 - std::pow(0.999, (double)t->step);
-    adam_kernel<<<(t->total + 255) / 256, 256, 0, st>>>(P, G, t->m.p, t->v.p, g_sumsq, 8, t->rnn_end, t->sigma_begin,
+    adam_kernel<<<(t->total + 255) / 256, 256, 0, st>>>(P, G, t->m.p, t->v.p, g_sumsq, nrs, t->rnn_end, t->sigma_begin,
                                                         t->total, t->hp.grad_max_norm,
                                                         (float)((double)t->hp.learning_rate / bc1),
                                                         (float)std::sqrt(bc2), t->hp.train_sigma2);
@@ -773,27 +817,44 @@ int finish_step(uis_trainer* t, cudaStream_t st, int mode, float* losses_out) {
 
 extern "C" {
 
-int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float* const* params /*[10] host*/,
+int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float* const* params /*[4 * depth + 6] host*/,
                        const uis_train_hparams* hp) {
   if (!out || !params || !hp) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   *out = nullptr;
   if (D < 1 || H < 1 || H > 4096 || D > 4096) return uis::api_fail(UIS_ERR_INVALID, "bad shape");
+  const int depth = hp->rnn_depth <= 0 ? 1 : hp->rnn_depth;
+  if (depth > kMaxTrainDepth)
+    return uis::api_fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the training kernels take 1..%d stacked GRU layers", depth, kMaxTrainDepth);
+  if (!(hp->rnn_dropout >= 0.f && hp->rnn_dropout < 1.f)) return uis::api_fail(UIS_ERR_INVALID, "rnn_dropout must be in [0, 1)");
   uis::DeviceGuard device_guard_(device);
   CUT(device_guard_.status);
   uis_trainer* t = new uis_trainer();
-  t->device = device; t->D = D; t->H = H; t->hp = *hp;
-  const int sizes[SEG_COUNT] = {3 * H * D, 3 * H * H, 3 * H, 3 * H, H * H, H, D * H, D, H, D};
+  t->device = device; t->D = D; t->H = H; t->hp = *hp; t->depth = depth;
+  t->n_seg = 4 * depth + 6; t->n_rnn_seg = 4 * depth + 4;
+  int sizes[kMaxSegs];
+  for (int l = 0; l < depth; ++l) {
+    sizes[t->seg_wih(l)] = 3 * H * (l == 0 ? D : H);
+    sizes[t->seg_whh(l)] = 3 * H * H;
+    sizes[t->seg_bih(l)] = 3 * H;
+    sizes[t->seg_bhh(l)] = 3 * H;
+  }
+  sizes[t->seg_w1()] = H * H; sizes[t->seg_b1()] = H; sizes[t->seg_w2()] = D * H; sizes[t->seg_b2()] = D;
+  sizes[t->seg_h0()] = depth * H; sizes[t->seg_sigma2()] = D;
   t->seg_off_h[0] = 0;
-  for (int s = 0; s < SEG_COUNT; ++s) t->seg_off_h[s + 1] = t->seg_off_h[s] + sizes[s];
-  t->total = t->seg_off_h[SEG_COUNT];
-  t->rnn_end = t->seg_off_h[SEG_H0];
-  t->sigma_begin = t->seg_off_h[SEG_SIGMA2];
+  for (int s = 0; s < t->n_seg; ++s) t->seg_off_h[s + 1] = t->seg_off_h[s] + sizes[s];
+  t->total = t->seg_off_h[t->n_seg];
+  t->rnn_end = t->seg_off_h[t->seg_h0()];
+  t->sigma_begin = t->seg_off_h[t->seg_sigma2()];
+  {
+    const char* env = std::getenv("UISRNN_B200_TRAIN_BARRIER");
+    t->spin_barrier = (env && std::strcmp(env, "spin") == 0) ? 1 : 0;
+  }
   auto body = [&]() -> int {
     if (int rc = t->params.ensure(t->total)) return rc;
     if (int rc = t->grads.ensure(t->total)) return rc;
     if (int rc = t->m.ensure(t->total)) return rc;
     if (int rc = t->v.ensure(t->total)) return rc;
-    for (int s = 0; s < SEG_COUNT; ++s) {
+    for (int s = 0; s < t->n_seg; ++s) {
       if (!params[s]) return uis::api_fail(UIS_ERR_INVALID, "NULL parameter %d", s);
       CUT(cudaMemcpy(t->params.p + t->seg_off_h[s], params[s], (size_t)sizes[s] * 4, cudaMemcpyDefault));
     }
@@ -801,7 +862,7 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
     CUT(cudaMemset(t->v.p, 0, (size_t)t->total * 4));
     CUT(cudaMalloc(&t->seg_off_d, sizeof(t->seg_off_h)));
     CUT(cudaMemcpy(t->seg_off_d, t->seg_off_h, sizeof(t->seg_off_h), cudaMemcpyHostToDevice));
-    CUT(cudaMalloc(&t->small, (size_t)(2 * D + 64) * 4));
+    CUT(cudaMalloc(&t->small, (size_t)(2 * D + 128) * 4));
     CUT(cudaMalloc(&t->tickets, 256 * sizeof(unsigned)));
     CUT(cudaMemset(t->tickets, 0, 256 * sizeof(unsigned)));
     CUT(cudaMalloc(&t->gemm_tickets, 4096 * sizeof(unsigned)));
@@ -819,7 +880,7 @@ int uis_trainer_destroy(uis_trainer* t) {
   if (!t) return 0;
   uis::DeviceGuard device_guard_(t->device);
   uis::DBuf* bufs[] = {&t->params, &t->grads, &t->m, &t->v, &t->segbuf, &t->x, &t->gi, &t->hs, &t->r, &t->z, &t->n,
-                       &t->hn, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
+                       &t->hn, &t->xin, &t->a1, &t->mu, &t->diff, &t->dmu, &t->dz1, &t->dout, &t->dgi, &t->dgh, &t->carry, &t->whh_t, &t->ghbuf,
                        &t->partial, &t->skpart, &t->gemm_partial, &t->loss_hist};
   for (auto* b : bufs) b->release();
   if (t->seg_off_d) cudaFree(t->seg_off_d);
@@ -876,7 +937,7 @@ int seq_check(uis_trainer* t) {
 }
 
 int check_lengths(const int32_t* lengths, int B, int L) {
-  if (B < 1 || B > 32) return uis::api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
+  if (B < 1 || B > (1 << 20)) return uis::api_fail(UIS_ERR_INVALID, "batch width %d", B);
   if (L < 2) return uis::api_fail(UIS_ERR_INVALID, "L < 2");
   for (int b = 0; b < B; ++b) {
     if (lengths[b] < 1 || lengths[b] > L || (b > 0 && lengths[b] > lengths[b - 1]) || (b == 0 && lengths[0] != L))
@@ -885,7 +946,7 @@ int check_lengths(const int32_t* lengths, int B, int L) {
   return 0;
 }
 int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode, float* losses_out, cudaStream_t st,
-                  const float* x_host, const uis::GatherCols* cols);
+                  const float* x_host, const long long* col_begin);
 }  // namespace
 
 // One iteration on a host batch.  x_host: fp32 [L][B][D] zero-padded (row 0 = zero frame), lengths[B] sorted
@@ -941,20 +1002,19 @@ int uis_trainer_set_corpus(uis_trainer* t, const double* rows, int64_t n_rows, c
 int uis_trainer_step_corpus(uis_trainer* t, const int32_t* chosen, int B, int mode, float* losses_out, void* stream) {
   if (!t || !chosen) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   if (t->sub_off.empty()) return uis::api_fail(UIS_ERR_INVALID, "uis_trainer_set_corpus has not been called");
-  if (B < 1 || B > 32) return uis::api_fail(UIS_ERR_UNSUPPORTED, "batch_size=%d: the training kernels take 1..32 sequences", B);
-  uis::GatherCols cols{};
-  int32_t lengths[32];
+  if (B < 1 || B > (1 << 20)) return uis::api_fail(UIS_ERR_INVALID, "batch width %d", B);
+  std::vector<long long> begin(B);
+  std::vector<int32_t> lengths(B);
   const long long n_sub = (long long)t->sub_off.size() - 1;
   for (int b = 0; b < B; ++b) {
     if (chosen[b] < 0 || chosen[b] >= n_sub) return uis::api_fail(UIS_ERR_INVALID, "sub-sequence id out of range");
-    cols.begin[b] = t->sub_off[chosen[b]];
+    begin[b] = t->sub_off[chosen[b]];
     lengths[b] = (int32_t)(t->sub_off[chosen[b] + 1] - t->sub_off[chosen[b]]) + 1;  // + the zero frame
-    cols.length[b] = lengths[b];
   }
-  if (int rc = check_lengths(lengths, B, lengths[0])) return rc;
+  if (int rc = check_lengths(lengths.data(), B, lengths[0])) return rc;
   uis::DeviceGuard device_guard_(t->device);
   CUT(device_guard_.status);
-  return run_iteration(t, lengths, B, lengths[0], mode, losses_out, static_cast<cudaStream_t>(stream), nullptr, &cols);
+  return run_iteration(t, lengths.data(), B, lengths[0], mode, losses_out, static_cast<cudaStream_t>(stream), nullptr, begin.data());
 }
 
 }  // extern "C"
@@ -965,41 +1025,57 @@ namespace {
 // mode 0: full step (forward, backward, clip, Adam); mode 1: forward + backward only (gradients can be read
 // back with uis_trainer_get, for tests); mode 2: data-parallel shard.
 int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode, float* losses_out, cudaStream_t st,
-                  const float* x_host, const uis::GatherCols* cols) {
+                  const float* x_host, const long long* col_begin) {
   using namespace uis;
-  const int D = t->D, H = t->H;
+  const int D = t->D, H = t->H, depth = t->depth;
   const size_t R = (size_t)L * B;
+  const size_t RH = R * H, RB = (R + B) * H;  // per-layer slab sizes (hs has one extra time step: h_{-1})
   if (int rc = t->x.ensure(R * D)) return rc;
-  if (int rc = t->gi.ensure(R * 3 * H)) return rc;
-  if (int rc = t->hs.ensure((R + B) * H)) return rc;
-  if (int rc = t->r.ensure(R * H)) return rc;
-  if (int rc = t->z.ensure(R * H)) return rc;
-  if (int rc = t->n.ensure(R * H)) return rc;
-  if (int rc = t->hn.ensure(R * H)) return rc;
-  if (int rc = t->a1.ensure(R * H)) return rc;
+  if (int rc = t->gi.ensure((size_t)depth * R * 3 * H)) return rc;
+  if (int rc = t->hs.ensure((size_t)depth * RB)) return rc;
+  if (int rc = t->r.ensure((size_t)depth * RH)) return rc;
+  if (int rc = t->z.ensure((size_t)depth * RH)) return rc;
+  if (int rc = t->n.ensure((size_t)depth * RH)) return rc;
+  if (int rc = t->hn.ensure((size_t)depth * RH)) return rc;
+  const bool drop = depth > 1 && t->hp.rnn_dropout > 0.f;
+  if (drop)
+    if (int rc = t->xin.ensure((size_t)(depth - 1) * RH)) return rc;
+  if (int rc = t->a1.ensure(RH)) return rc;
   if (int rc = t->mu.ensure(R * D)) return rc;
   if (int rc = t->diff.ensure(R * D)) return rc;
   if (int rc = t->dmu.ensure(R * D)) return rc;
-  if (int rc = t->dz1.ensure(R * H)) return rc;
-  if (int rc = t->dout.ensure(R * H)) return rc;
+  if (int rc = t->dz1.ensure(RH)) return rc;
+  if (int rc = t->dout.ensure(RH)) return rc;
   if (int rc = t->dgi.ensure(R * 3 * H)) return rc;
   if (int rc = t->dgh.ensure(R * 3 * H)) return rc;
   if (int rc = t->carry.ensure((size_t)B * H)) return rc;
   if (int rc = t->whh_t.ensure((size_t)3 * H * H)) return rc;
   if (int rc = t->ghbuf.ensure((size_t)32 * 3 * H)) return rc;
-  if (int rc = t->partial.ensure((size_t)16 * kSumsqBlocks)) return rc;
+  if (int rc = t->partial.ensure((size_t)32 * kSumsqBlocks)) return rc;
   if (int rc = t->skpart.ensure((size_t)((3 * H + 63) / 64) * kSplit * 32 * 64)) return rc;
   if ((3 * H + 63) / 64 > 256) return api_fail(UIS_ERR_UNSUPPORTED, "hidden size too large for the training kernels");
+  if (R * 3 * H > (size_t)0x7fffffff) return api_fail(UIS_ERR_UNSUPPORTED, "batch of %d x %d rows is too large", L, B);
   float* P = t->params.p;
   float* G = t->grads.p;
   const int* so = t->seg_off_h;
   float* sum_sq_d = t->small; float* cnt_d = t->small + D; float* nz = t->small + 2 * D;
   float* scalars = nz + 1;
-  std::vector<int> nb(L);
-  for (int tt = 0; tt < L; ++tt) { int c = 0; while (c < B && lengths[c] > tt) ++c; nb[tt] = c; }
+  // batch columns are processed by the recurrence in groups of <= 32 (one warp lane per column)
+  const int n_groups = (B + 31) / 32;
+  auto group_rows = [&](int g, int tt) {  // live columns of group g at time tt (lengths are sorted descending)
+    const int b0 = 32 * g, nbg = std::min(32, B - b0);
+    int c = 0;
+    while (c < nbg && lengths[b0 + c] > tt) ++c;
+    return c;
+  };
 
-  if (cols) {
-    gather_batch_kernel<<<(unsigned)R, 128, 0, st>>>(t->corpus.p, t->corpus_index, *cols, t->x.p, L, B, D);
+  if (col_begin) {
+    for (int g = 0; g < n_groups; ++g) {
+      const int b0 = 32 * g, nbg = std::min(32, B - b0);
+      GatherCols cols{};
+      for (int b = 0; b < nbg; ++b) { cols.begin[b] = col_begin[b0 + b]; cols.length[b] = lengths[b0 + b]; }
+      gather_batch_kernel<<<(unsigned)(L * nbg), 128, 0, st>>>(t->corpus.p, t->corpus_index, cols, t->x.p, nbg, b0, B, D);
+    }
     CUT(cudaGetLastError());
   } else {  // stage the batch in pinned memory: the H2D copy then overlaps the previous iteration's kernels
     const size_t bytes = R * D * 4;
@@ -1020,49 +1096,79 @@ int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode
     CUT(cudaMemcpyAsync(t->x.p, t->pin[pi], bytes, cudaMemcpyHostToDevice, st));
     CUT(cudaEventRecord(t->pin_ev[pi], st));
   }
-  CUT(cudaMemsetAsync(t->hs.p, 0, (R + B) * H * 4, st));
-  CUT(cudaMemsetAsync(t->small, 0, (size_t)(2 * D + 64) * 4, st));
+  CUT(cudaMemsetAsync(t->hs.p, 0, (size_t)depth * RB * 4, st));
+  CUT(cudaMemsetAsync(t->small, 0, (size_t)(2 * D + 128) * 4, st));
   CUT(cudaMemsetAsync(G, 0, (size_t)t->total * 4, st));
-  CUT(cudaMemsetAsync(t->carry.p, 0, (size_t)B * H * 4, st));
   CUT(cudaMemsetAsync(t->dgi.p, 0, R * 3 * H * 4, st));
   CUT(cudaMemsetAsync(t->dgh.p, 0, R * 3 * H * 4, st));
-  // h_{-1} = rnn_init_hidden repeated over the batch (uisrnn.py:262)
-  for (int b = 0; b < B; ++b)
-    CUT(cudaMemcpyAsync(t->hs.p + (size_t)b * H, P + so[SEG_H0], (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
-
-  // ---- forward
-  if (int rc = gemm<false, true>(st, t->sc, t->x.p, P + so[SEG_WIH], P + so[SEG_BIH], nullptr, t->gi.p, (int)R, 3 * H, D)) return rc;
+  // h_{-1} of layer l = rnn_init_hidden[l] repeated over the batch (uisrnn.py:262)
+  for (int l = 0; l < depth; ++l)
+    for (int b = 0; b < B; ++b)
+      CUT(cudaMemcpyAsync(t->hs.p + (size_t)l * RB + (size_t)b * H, P + so[t->seg_h0()] + (size_t)l * H, (size_t)H * 4,
+                          cudaMemcpyDeviceToDevice, st));
   if (t->seq_mode < 0) {
     if (int rc = seq_setup(t)) return rc;
   }
-  SeqParams sp{};
-  for (int b = 0; b < 32; ++b) sp.length[b] = b < B ? lengths[b] : 0;
-  sp.L = L; sp.B = B; sp.H = H;
-  if (t->seq_mode == 1) {
-    CUT(cudaMemsetAsync(t->seq_bar, 0, 2 * sizeof(unsigned), st));
-    const float* a_whh = P + so[SEG_WHH]; const float* a_bhh = P + so[SEG_BHH]; const float* a_gi = t->gi.p;
-    float* a_hs = t->hs.p; float* a_r = t->r.p; float* a_z = t->z.p; float* a_n = t->n.p; float* a_hn = t->hn.p;
-    unsigned* a_bar = t->seq_bar; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
-    void* args[] = {&a_whh, &a_bhh, &a_gi, &a_hs, &a_r, &a_z, &a_n, &a_hn, &sp, &a_bar, &a_err};
-    CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_fwd_kernel, dim3(H / kUPC), dim3(256), args, seq_fwd_smem(H), st));
-  } else {
-    // k-major copy of W_hh for the recurrent products (the weights change every iteration)
-    dim3 tg((H + 31) / 32, (3 * H + 31) / 32), tb(32, 8);
-    transpose_kernel<<<tg, tb, 0, st>>>(P + so[SEG_WHH], t->whh_t.p, 3 * H, H);
-    for (int tt = 0; tt < L; ++tt) {
-      if (nb[tt] == 0) break;
-      const size_t o = (size_t)tt * B;
-      splitk_gemm_kernel<<<dim3((3 * H + 63) / 64, kSplit), 256, 0, st>>>(t->hs.p + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H,
-                                                                          nb[tt], 3 * H, H, 0, t->skpart.p, t->tickets);
-      gru_gate_fwd_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, P + so[SEG_BHH], t->gi.p + o * 3 * H,
-                                                                    t->hs.p + o * H, t->hs.p + (o + B) * H, t->r.p + o * H,
-                                                                    t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H, nb[tt], H);
+  const unsigned it_no = (unsigned)t->calls;  // dropout masks: a function of (seed, iteration, layer, element)
+  const unsigned seed = (unsigned)(t->hp.dropout_seed ^ (t->hp.dropout_seed >> 32));
+  const float keep_inv = drop ? 1.0f / (1.0f - t->hp.rnn_dropout) : 1.0f;
+  const int drop_blocks = (int)std::min<size_t>((RH + 255) / 256, 148 * 8);
+  // input sequence of layer l: the batch itself, or the (dropped) output sequence of the layer below
+  auto layer_in = [&](int l) -> const float* {
+    if (l == 0) return t->x.p;
+    return drop ? t->xin.p + (size_t)(l - 1) * RH : t->hs.p + (size_t)(l - 1) * RB + (size_t)B * H;
+  };
+
+  // ---- forward
+  for (int l = 0; l < depth; ++l) {
+    float* gi_l = t->gi.p + (size_t)l * R * 3 * H;
+    float* hs_l = t->hs.p + (size_t)l * RB;
+    float* r_l = t->r.p + (size_t)l * RH; float* z_l = t->z.p + (size_t)l * RH;
+    float* n_l = t->n.p + (size_t)l * RH; float* hn_l = t->hn.p + (size_t)l * RH;
+    const float* whh = P + so[t->seg_whh(l)];
+    const float* bhh = P + so[t->seg_bhh(l)];
+    if (int rc = gemm<false, true>(st, t->sc, layer_in(l), P + so[t->seg_wih(l)], P + so[t->seg_bih(l)], nullptr, gi_l, (int)R,
+                                   3 * H, l == 0 ? D : H)) return rc;
+    if (t->seq_mode == 0) {  // k-major copy of W_hh for the per-step recurrent products (the weights change every iteration)
+      dim3 tg((H + 31) / 32, (3 * H + 31) / 32), tb(32, 8);
+      transpose_kernel<<<tg, tb, 0, st>>>(whh, t->whh_t.p, 3 * H, H);
+    }
+    for (int g = 0; g < n_groups; ++g) {
+      const int b0 = 32 * g, nbg = std::min(32, B - b0), Lg = lengths[b0];
+      if (t->seq_mode == 1) {
+        SeqParams sp{};
+        for (int b = 0; b < 32; ++b) sp.length[b] = b < nbg ? lengths[b0 + b] : 0;
+        sp.L = Lg; sp.B = nbg; sp.H = H; sp.stride = B; sp.spin_barrier = t->spin_barrier;
+        CUT(cudaMemsetAsync(t->seq_bar, 0, 2 * sizeof(unsigned), st));
+        const float* a_whh = whh; const float* a_bhh = bhh; const float* a_gi = gi_l + (size_t)b0 * 3 * H;
+        float* a_hs = hs_l + (size_t)b0 * H; float* a_r = r_l + (size_t)b0 * H; float* a_z = z_l + (size_t)b0 * H;
+        float* a_n = n_l + (size_t)b0 * H; float* a_hn = hn_l + (size_t)b0 * H;
+        unsigned* a_bar = t->seq_bar; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
+        void* args[] = {&a_whh, &a_bhh, &a_gi, &a_hs, &a_r, &a_z, &a_n, &a_hn, &sp, &a_bar, &a_err};
+        CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_fwd_kernel, dim3(H / kUPC), dim3(256), args, seq_fwd_smem(H), st));
+      } else {
+        for (int tt = 0; tt < Lg; ++tt) {
+          const int nb = group_rows(g, tt);
+          if (nb == 0) break;
+          const size_t o = (size_t)tt * B + b0;
+          splitk_gemm_kernel<<<dim3((3 * H + 63) / 64, kSplit), 256, 0, st>>>(hs_l + o * H, H, t->whh_t.p, t->ghbuf.p, 3 * H,
+                                                                              nb, 3 * H, H, 0, t->skpart.p, t->tickets);
+          gru_gate_fwd_kernel<<<(nb * H + 255) / 256, 256, 0, st>>>(t->ghbuf.p, bhh, gi_l + o * 3 * H, hs_l + o * H,
+                                                                    hs_l + (o + B) * H, r_l + o * H, z_l + o * H,
+                                                                    n_l + o * H, hn_l + o * H, nb, H);
+        }
+      }
+    }
+    CUT(cudaGetLastError());
+    if (drop && l + 1 < depth) {
+      dropout_kernel<<<drop_blocks, 256, 0, st>>>(hs_l + (size_t)B * H, t->xin.p + (size_t)l * RH, RH, seed, it_no, (unsigned)l,
+                                                 t->hp.rnn_dropout, keep_inv);
+      CUT(cudaGetLastError());
     }
   }
-  CUT(cudaGetLastError());
-  const float* out = t->hs.p + (size_t)B * H;  // out[t] = h_t ; padded rows stay zero
-  if (int rc = gemm<false, true>(st, t->sc, out, P + so[SEG_W1], P + so[SEG_B1], nullptr, t->a1.p, (int)R, H, H, true)) return rc;
-  if (int rc = gemm<false, true>(st, t->sc, t->a1.p, P + so[SEG_W2], P + so[SEG_B2], nullptr, t->mu.p, (int)R, D, H)) return rc;
+  const float* out = t->hs.p + (size_t)(depth - 1) * RB + (size_t)B * H;  // out[t] = h_t of the top layer; padded rows stay zero
+  if (int rc = gemm<false, true>(st, t->sc, out, P + so[t->seg_w1()], P + so[t->seg_b1()], nullptr, t->a1.p, (int)R, H, H, true)) return rc;
+  if (int rc = gemm<false, true>(st, t->sc, t->a1.p, P + so[t->seg_w2()], P + so[t->seg_b2()], nullptr, t->mu.p, (int)R, D, H)) return rc;
   const int bd_blocks = (B * D + 255) / 256;
   loss_fwd_kernel<<<bd_blocks, 256, 0, st>>>(t->mu.p, t->x.p, t->diff.p, sum_sq_d, cnt_d, nz, L, B, D);
   // mode 2 (data-parallel shard): the row count is global, so gradients are accumulated WITHOUT the 1/nz
@@ -1072,44 +1178,69 @@ int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode
     set_scalar_kernel<<<1, 1, 0, st>>>(scalars + 3, 1.0f);  // (a pageable H2D copy would synchronise the stream)
     nz_for_bwd = scalars + 3;
   } else {
-    loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[SEG_SIGMA2], t->hp.sigma_alpha, t->hp.sigma_beta,
-                                         G + so[SEG_SIGMA2], scalars, D);
+    loss_scalar_kernel<<<1, 256, 0, st>>>(sum_sq_d, cnt_d, nz, P + so[t->seg_sigma2()], t->hp.sigma_alpha, t->hp.sigma_beta,
+                                         G + so[t->seg_sigma2()], scalars, D);
   }
   // ---- backward
-  loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[SEG_SIGMA2], nz_for_bwd, t->dmu.p, L, B, D);
+  loss_bwd_kernel<<<bd_blocks, 256, 0, st>>>(t->diff.p, P + so[t->seg_sigma2()], nz_for_bwd, t->dmu.p, L, B, D);
   CUT(cudaGetLastError());
-  if (int rc = gemm<true, false>(st, t->sc, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[SEG_W2], D, H, (int)R)) return rc;
-  colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(t->dmu.p, G + so[SEG_B2], (int)R, D);
-  if (int rc = gemm<false, false>(st, t->sc, t->dmu.p, P + so[SEG_W2], nullptr, t->a1.p, t->dz1.p, (int)R, H, D)) return rc;  // * relu'
-  if (int rc = gemm<true, false>(st, t->sc, t->dz1.p, out, nullptr, nullptr, G + so[SEG_W1], H, H, (int)R)) return rc;
-  colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dz1.p, G + so[SEG_B1], (int)R, H);
-  if (int rc = gemm<false, false>(st, t->sc, t->dz1.p, P + so[SEG_W1], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
-  if (t->seq_mode == 1) {
-    const float* a_whh = P + so[SEG_WHH]; const float* a_dout = t->dout.p; const float* a_r = t->r.p;
-    const float* a_z = t->z.p; const float* a_n = t->n.p; const float* a_hn = t->hn.p; const float* a_hs = t->hs.p;
-    float* a_dgi = t->dgi.p; float* a_dgh = t->dgh.p; float* a_carry = t->carry.p;
-    unsigned* a_bar = t->seq_bar + 1; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
-    void* args[] = {&a_whh, &a_dout, &a_r, &a_z, &a_n, &a_hn, &a_hs, &a_dgi, &a_dgh, &a_carry, &sp, &a_bar, &a_err};
-    CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_bwd_kernel, dim3(H / kUPC), dim3(256), args, seq_bwd_smem(H), st));
-  } else {
-    for (int tt = L - 1; tt >= 0; --tt) {
-      if (nb[tt] == 0) continue;
-      const size_t o = (size_t)tt * B;
-      gru_bwd_step_kernel<<<(nb[tt] * H + 255) / 256, 256, 0, st>>>(t->dout.p + o * H, t->carry.p, t->r.p + o * H,
-                                                                    t->z.p + o * H, t->n.p + o * H, t->hn.p + o * H,
-                                                                    t->hs.p + o * H, t->dgi.p + o * 3 * H,
-                                                                    t->dgh.p + o * 3 * H, nb[tt], H);
-      // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
-      splitk_gemm_kernel<<<dim3((H + 63) / 64, kSplit), 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, P + so[SEG_WHH], t->carry.p,
-                                                                      H, nb[tt], H, 3 * H, 1, t->skpart.p, t->tickets);
+  if (int rc = gemm<true, false>(st, t->sc, t->dmu.p, t->a1.p, nullptr, nullptr, G + so[t->seg_w2()], D, H, (int)R)) return rc;
+  colsum_kernel<<<(D + 31) / 32, 256, 0, st>>>(t->dmu.p, G + so[t->seg_b2()], (int)R, D);
+  if (int rc = gemm<false, false>(st, t->sc, t->dmu.p, P + so[t->seg_w2()], nullptr, t->a1.p, t->dz1.p, (int)R, H, D)) return rc;  // * relu'
+  if (int rc = gemm<true, false>(st, t->sc, t->dz1.p, out, nullptr, nullptr, G + so[t->seg_w1()], H, H, (int)R)) return rc;
+  colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->dz1.p, G + so[t->seg_b1()], (int)R, H);
+  if (int rc = gemm<false, false>(st, t->sc, t->dz1.p, P + so[t->seg_w1()], nullptr, nullptr, t->dout.p, (int)R, H, H)) return rc;
+  for (int l = depth - 1; l >= 0; --l) {  // dout = gradient w.r.t. the output sequence of layer l
+    const float* hs_l = t->hs.p + (size_t)l * RB;
+    const float* r_l = t->r.p + (size_t)l * RH; const float* z_l = t->z.p + (size_t)l * RH;
+    const float* n_l = t->n.p + (size_t)l * RH; const float* hn_l = t->hn.p + (size_t)l * RH;
+    const float* whh = P + so[t->seg_whh(l)];
+    CUT(cudaMemsetAsync(t->carry.p, 0, (size_t)B * H * 4, st));
+    for (int g = 0; g < n_groups; ++g) {
+      const int b0 = 32 * g, nbg = std::min(32, B - b0), Lg = lengths[b0];
+      if (t->seq_mode == 1) {
+        SeqParams sp{};
+        for (int b = 0; b < 32; ++b) sp.length[b] = b < nbg ? lengths[b0 + b] : 0;
+        sp.L = Lg; sp.B = nbg; sp.H = H; sp.stride = B; sp.spin_barrier = t->spin_barrier;
+        CUT(cudaMemsetAsync(t->seq_bar, 0, 2 * sizeof(unsigned), st));
+        const float* a_whh = whh; const float* a_dout = t->dout.p + (size_t)b0 * H; const float* a_r = r_l + (size_t)b0 * H;
+        const float* a_z = z_l + (size_t)b0 * H; const float* a_n = n_l + (size_t)b0 * H; const float* a_hn = hn_l + (size_t)b0 * H;
+        const float* a_hs = hs_l + (size_t)b0 * H;
+        float* a_dgi = t->dgi.p + (size_t)b0 * 3 * H; float* a_dgh = t->dgh.p + (size_t)b0 * 3 * H;
+        float* a_carry = t->carry.p + (size_t)b0 * H;
+        unsigned* a_bar = t->seq_bar + 1; int* a_err = reinterpret_cast<int*>(t->seq_bar + 2);
+        void* args[] = {&a_whh, &a_dout, &a_r, &a_z, &a_n, &a_hn, &a_hs, &a_dgi, &a_dgh, &a_carry, &sp, &a_bar, &a_err};
+        CUT(cudaLaunchCooperativeKernel((const void*)gru_seq_bwd_kernel, dim3(H / kUPC), dim3(256), args, seq_bwd_smem(H), st));
+      } else {
+        for (int tt = Lg - 1; tt >= 0; --tt) {
+          const int nb = group_rows(g, tt);
+          if (nb == 0) continue;
+          const size_t o = (size_t)tt * B + b0;
+          gru_bwd_step_kernel<<<(nb * H + 255) / 256, 256, 0, st>>>(t->dout.p + o * H, t->carry.p + (size_t)b0 * H, r_l + o * H,
+                                                                    z_l + o * H, n_l + o * H, hn_l + o * H, hs_l + o * H,
+                                                                    t->dgi.p + o * 3 * H, t->dgh.p + o * 3 * H, nb, H);
+          // carry[b] += dGh_t[b] * W_hh   (W_hh stored [3H][H] = [K][N])
+          splitk_gemm_kernel<<<dim3((H + 63) / 64, kSplit), 256, 0, st>>>(t->dgh.p + o * 3 * H, 3 * H, whh,
+                                                                          t->carry.p + (size_t)b0 * H, H, nb, H, 3 * H, 1,
+                                                                          t->skpart.p, t->tickets);
+        }
+      }
+    }
+    CUT(cudaGetLastError());
+    if (int rc = gemm<true, false>(st, t->sc, t->dgi.p, layer_in(l), nullptr, nullptr, G + so[t->seg_wih(l)], 3 * H,
+                                   l == 0 ? D : H, (int)R)) return rc;
+    if (int rc = gemm<true, false>(st, t->sc, t->dgh.p, hs_l, nullptr, nullptr, G + so[t->seg_whh(l)], 3 * H, H, (int)R)) return rc;
+    colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgi.p, G + so[t->seg_bih(l)], (int)R, 3 * H);
+    colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[t->seg_bhh(l)], (int)R, 3 * H);
+    colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[t->seg_h0()] + (size_t)l * H, B, H);  // d h0 = sum_b d h_{-1}
+    if (l > 0) {  // gradient w.r.t. this layer's input sequence = (through the dropout mask) the output of layer l - 1
+      if (int rc = gemm<false, false>(st, t->sc, t->dgi.p, P + so[t->seg_wih(l)], nullptr, nullptr, t->dout.p, (int)R, H, 3 * H)) return rc;
+      if (drop) {
+        dropout_kernel<<<drop_blocks, 256, 0, st>>>(t->dout.p, t->dout.p, RH, seed, it_no, (unsigned)(l - 1), t->hp.rnn_dropout, keep_inv);
+        CUT(cudaGetLastError());
+      }
     }
   }
-  CUT(cudaGetLastError());
-  if (int rc = gemm<true, false>(st, t->sc, t->dgi.p, t->x.p, nullptr, nullptr, G + so[SEG_WIH], 3 * H, D, (int)R)) return rc;
-  if (int rc = gemm<true, false>(st, t->sc, t->dgh.p, t->hs.p, nullptr, nullptr, G + so[SEG_WHH], 3 * H, H, (int)R)) return rc;
-  colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgi.p, G + so[SEG_BIH], (int)R, 3 * H);
-  colsum_kernel<<<(3 * H + 31) / 32, 256, 0, st>>>(t->dgh.p, G + so[SEG_BHH], (int)R, 3 * H);
-  colsum_kernel<<<(H + 31) / 32, 256, 0, st>>>(t->carry.p, G + so[SEG_H0], B, H);  // d h0 = sum_b d h_{-1}
   if (mode == 2) return 0;  // gradients + statistics stay on the device for uis_trainer_comm_export()
   return finish_step(t, st, mode, losses_out);
 }
@@ -1156,14 +1287,14 @@ int uis_trainer_comm_apply(uis_trainer* t, const float* dev_buf, void* stream) {
   CUT(cudaMemcpyAsync(t->small, dev_buf + t->sigma_begin, (size_t)(2 * D + 1) * 4, cudaMemcpyDeviceToDevice, st));
   float* nz = t->small + 2 * D;
   uis::scale_by_inv_kernel<<<(t->sigma_begin + 255) / 256, 256, 0, st>>>(t->grads.p, nz, t->sigma_begin);
-  uis::loss_scalar_kernel<<<1, 256, 0, st>>>(t->small, t->small + D, nz, t->params.p + t->seg_off_h[SEG_SIGMA2],
-                                            t->hp.sigma_alpha, t->hp.sigma_beta, t->grads.p + t->seg_off_h[SEG_SIGMA2],
+  uis::loss_scalar_kernel<<<1, 256, 0, st>>>(t->small, t->small + D, nz, t->params.p + t->seg_off_h[t->seg_sigma2()],
+                                            t->hp.sigma_alpha, t->hp.sigma_beta, t->grads.p + t->seg_off_h[t->seg_sigma2()],
                                             nz + 1, D);
   CUT(cudaGetLastError());
   return finish_step(t, st, 0, nullptr);
 }
 
-// what: 0 = parameters, 1 = gradients of the last step.  out[10] host buffers (any may be NULL).
+// what: 0 = parameters, 1 = gradients of the last step.  out[4 * depth + 6] host buffers (any may be NULL).
 int uis_trainer_get(uis_trainer* t, int what, float* const* out) {
   if (!t || !out) return uis::api_fail(UIS_ERR_INVALID, "null argument");
   uis::DeviceGuard device_guard_(t->device);
@@ -1171,7 +1302,7 @@ int uis_trainer_get(uis_trainer* t, int what, float* const* out) {
   CUT(cudaDeviceSynchronize());
   if (int rc = seq_check(t)) return rc;
   const float* src = what == 0 ? t->params.p : t->grads.p;
-  for (int s = 0; s < SEG_COUNT; ++s)
+  for (int s = 0; s < t->n_seg; ++s)
     if (out[s])
       CUT(cudaMemcpy(out[s], src + t->seg_off_h[s], (size_t)(t->seg_off_h[s + 1] - t->seg_off_h[s]) * 4,
                      cudaMemcpyDeviceToHost));

@@ -20,7 +20,7 @@ UIS_ERR_CUDA = -3
 UIS_ERR_OVERFLOW = -4
 UIS_ERR_NOMEM = -5
 UIS_ERR_CAPACITY = -6
-UIS_ABI_VERSION = 3  # include/uisrnn_b200.h
+UIS_ABI_VERSION = 4  # include/uisrnn_b200.h
 
 
 class NativeError(RuntimeError):
@@ -48,7 +48,9 @@ class Stats(C.Structure):
               ('gru_columns', C.c_int64), ('weight_passes', C.c_int64), ('candidates', C.c_int64),
               ('kernel_launches', C.c_int64), ('ctas', C.c_int32), ('max_k', C.c_int32),
               ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('cluster', C.c_int32), ('engine', C.c_int32),
-              ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10), ('tc_cycles', C.c_int64 * 4)]
+              ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10), ('tc_cycles', C.c_int64 * 4),
+              ('h2d_ms', C.c_float), ('pipeline_ms', C.c_float), ('host_ms', C.c_float), ('chunks', C.c_int32),
+              ('groups', C.c_int32), ('reserved_', C.c_int32)]
 
   def as_dict(self):
     out = {}
@@ -70,12 +72,34 @@ EXPORTS = ('uis_version', 'uis_last_error', 'uis_model_create', 'uis_model_destr
 class TrainHParams(C.Structure):
   _fields_ = [('learning_rate', C.c_float), ('sigma_alpha', C.c_float), ('sigma_beta', C.c_float),
               ('regularization_weight', C.c_float), ('grad_max_norm', C.c_float),
-              ('train_sigma2', C.c_int32)]
+              ('train_sigma2', C.c_int32), ('rnn_depth', C.c_int32), ('rnn_dropout', C.c_float),
+              ('dropout_seed', C.c_int64)]
 
 
-PARAM_ORDER = ('gru.weight_ih_l0', 'gru.weight_hh_l0', 'gru.bias_ih_l0', 'gru.bias_hh_l0',
-               'linear_mean1.weight', 'linear_mean1.bias', 'linear_mean2.weight', 'linear_mean2.bias',
-               'rnn_init_hidden', 'sigma2')
+def param_order(depth=1):
+  """Names of the 4 * depth + 6 training tensors in the order uis_trainer_create takes them."""
+  names = []
+  for layer in range(depth):
+    names += ['gru.{}_l{}'.format(kind, layer) for kind in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')]
+  return tuple(names + ['linear_mean1.weight', 'linear_mean1.bias', 'linear_mean2.weight', 'linear_mean2.bias',
+                        'rnn_init_hidden', 'sigma2'])
+
+
+PARAM_ORDER = param_order(1)
+
+
+def dropout_keep_mask(seed, iteration, layer, count, p):
+  """The keep decisions of uis_train.cu's dropout_kernel for elements 0..count-1 (bool array): the same 32-bit
+  hash, restated in numpy -- used by the tests to rebuild the masks of a training iteration."""
+  seed = np.uint32((int(seed) ^ (int(seed) >> 32)) & 0xffffffff)
+  with np.errstate(over='ignore'):
+    i = np.arange(count, dtype=np.uint32)
+    h = seed ^ (np.uint32(iteration) * np.uint32(0x9E3779B1)) ^ (np.uint32(layer) * np.uint32(0x85EBCA77)) ^ \
+        (i * np.uint32(0xC2B2AE3D))
+    h ^= h >> np.uint32(16); h *= np.uint32(0x7FEB352D); h ^= h >> np.uint32(15); h *= np.uint32(0x846CA68B)
+    h ^= h >> np.uint32(16)
+  u = (h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+  return u >= np.float32(p)
 
 _lib = None
 
@@ -296,20 +320,24 @@ class NativeModel:
 class NativeTrainer:
   """Owns a `uis_trainer*`: parameters, gradients and Adam state of one fit_concatenated call live
   on the device; `step()` runs one iteration on a host batch.  `params`: dict name -> ndarray in
-  PARAM_ORDER (rnn_init_hidden flattened to [H])."""
+  param_order(depth) (rnn_init_hidden flattened to [depth * H]); hparams may carry rnn_depth (default 1),
+  rnn_dropout (default 0) and dropout_seed."""
 
   def __init__(self, params, hparams, device=0):
     lib = load_library()
     self._lib = lib
     self._h = C.c_void_p()
-    self.shapes = [tuple(np.asarray(params[k]).shape) for k in PARAM_ORDER]
-    arrs = [_f32(np.asarray(params[k]).reshape(-1)) for k in PARAM_ORDER]
+    self.depth = int(hparams.get('rnn_depth', 1) or 1)
+    self.order = param_order(self.depth)
+    self.shapes = [tuple(np.asarray(params[k]).shape) for k in self.order]
+    arrs = [_f32(np.asarray(params[k]).reshape(-1)) for k in self.order]
     self.H = int(np.asarray(params['linear_mean1.weight']).shape[0])
     self.D = int(np.asarray(params['linear_mean2.weight']).shape[0])
-    ptrs = (C.c_void_p * 10)(*[a.ctypes.data for a in arrs])
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     hp = TrainHParams(float(hparams['learning_rate']), float(hparams['sigma_alpha']),
                       float(hparams['sigma_beta']), float(hparams['regularization_weight']),
-                      float(hparams['grad_max_norm']), int(bool(hparams['train_sigma2'])))
+                      float(hparams['grad_max_norm']), int(bool(hparams['train_sigma2'])), self.depth,
+                      float(hparams.get('rnn_dropout', 0.0) or 0.0), int(hparams.get('dropout_seed', 0) or 0))
     _check(lib, lib.uis_trainer_create(C.byref(self._h), device, self.D, self.H, ptrs, C.byref(hp)))
 
   def close(self):
@@ -397,9 +425,9 @@ class NativeTrainer:
 
   def _get(self, what):
     outs = [np.empty(int(np.prod(s)) if s else 1, np.float32) for s in self.shapes]
-    ptrs = (C.c_void_p * 10)(*[o.ctypes.data for o in outs])
+    ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
     _check(self._lib, self._lib.uis_trainer_get(self._h, what, ptrs))
-    return {k: o.reshape(s) for k, o, s in zip(PARAM_ORDER, outs, self.shapes)}
+    return {k: o.reshape(s) for k, o, s in zip(self.order, outs, self.shapes)}
 
   def parameters(self):
     return self._get(0)

@@ -241,12 +241,13 @@ class UISRNN:
     random.setstate(rng[1])
 
   def _native_fit_supported(self, args):
-    """The hand-written training kernels (csrc/uis_train.cu) cover the default model family:
-    CUDA device, one GRU layer, mini-batches of 1..32 sequences.  Other configurations train with
-    PyTorch autograd on the model's device (same mathematics)."""
+    """On a CUDA device fit() runs on the hand-written training kernels (csrc/uis_train.cu): 1..4 stacked GRU
+    layers (inter-layer dropout in train mode), any mini-batch width including batch_size=None (one batch of
+    every sub-sequence).  UISRNN_B200_TORCH_FIT=1 selects PyTorch autograd instead (a developer switch for A/B
+    checks); the CPU device always trains with PyTorch, as the reference does."""
     import os
-    return (self.device.type == 'cuda' and self.rnn_init_hidden.shape[0] == 1 and
-            args.batch_size is not None and 1 <= args.batch_size <= 32 and
+    del args
+    return (self.device.type == 'cuda' and 1 <= self.rnn_init_hidden.shape[0] <= 4 and
             os.environ.get('UISRNN_B200_TORCH_FIT', '0') != '1')
 
   def _fit_native(self, train_sequence, index_lists, seq_lengths, args):
@@ -261,12 +262,20 @@ class UISRNN:
     # world > 1: data-parallel fit (optional) -- every rank holds rank 0's parameters and draws
     # the SAME mini-batches (_sync_replicas); rank r owns batch columns r, r + world, ...
     state = {k: v.detach().cpu().numpy() for k, v in self.rnn_model.state_dict().items()}
-    params = {name: state[name] for name in native.PARAM_ORDER[:8]}
+    depth = int(self.rnn_init_hidden.shape[0])
+    order = native.param_order(depth)
+    params = {name: state[name] for name in order[:-2]}
     params['rnn_init_hidden'] = self.rnn_init_hidden.detach().cpu().numpy().reshape(-1)
     params['sigma2'] = self.sigma2.detach().cpu().numpy()
+    # the dropout masks of the stacked GRU are seeded from torch's generator (so torch.manual_seed() makes a run
+    # repeatable, as it does for the reference), one draw per fit_concatenated call (in a data-parallel job every
+    # rank masks its own columns, so the ranks need not share the seed)
+    dropout = float(self.rnn_model.gru.dropout) if depth > 1 else 0.0
+    dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if dropout > 0 else 0
     hparams = {'learning_rate': args.learning_rate, 'sigma_alpha': args.sigma_alpha, 'sigma_beta': args.sigma_beta,
                'regularization_weight': args.regularization_weight, 'grad_max_norm': args.grad_max_norm,
-               'train_sigma2': self.estimate_sigma2}
+               'train_sigma2': self.estimate_sigma2, 'rnn_depth': depth, 'rnn_dropout': dropout,
+               'dropout_seed': dropout_seed}
     trainer = native.NativeTrainer(params, hparams, device=self.device.index or 0)
     self.last_training_losses = []
     self.last_training_loss_terms = []  # [iteration] -> (negative log likelihood, sigma2 prior, regularisation)
@@ -308,8 +317,8 @@ class UISRNN:
     finally:
       trainer.close()
     with torch.no_grad():
-      self.rnn_model.load_state_dict({k: torch.from_numpy(trained[k].copy()) for k in native.PARAM_ORDER[:8]})
-      self.rnn_init_hidden.data.copy_(torch.from_numpy(trained['rnn_init_hidden'].reshape(1, 1, -1)))
+      self.rnn_model.load_state_dict({k: torch.from_numpy(trained[k].copy()) for k in order[:-2]})
+      self.rnn_init_hidden.data.copy_(torch.from_numpy(trained['rnn_init_hidden'].reshape(depth, 1, -1)))
       self.sigma2.data.copy_(torch.from_numpy(trained['sigma2']))
     self._native = None
     self.logger.print(1, 'Done training with {} iterations'.format(args.train_iteration))
@@ -390,7 +399,7 @@ class UISRNN:
         self._native = (key, native.NativeModel(self.export_weights(), device=index))
       return self._native[1]
 
-  def _predict_cuda(self, sequences, args, device_index=None):
+  def _predict_cuda(self, sequences, args, device_index=None, as_arrays=False):
     from . import native
     model = self._native_model(device_index)
     kcap = _DEFAULT_KCAP
@@ -399,7 +408,7 @@ class UISRNN:
         with model.lock:  # a uis_model handle (one workspace) is not re-entrant
           labels = model.predict(sequences, beam_size=args.beam_size, look_ahead=args.look_ahead,
                                  test_iteration=args.test_iteration, kcap=kcap)
-        return [lab.tolist() for lab in labels]
+        return labels if as_arrays else [lab.tolist() for lab in labels]
       except native.NativeError as err:
         if err.code != native.UIS_ERR_OVERFLOW or kcap >= 1024:
           raise
