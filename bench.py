@@ -168,35 +168,6 @@ def host_info():
 def secondary_metrics(model, torch):
   """Best-effort extra numbers for the other BASELINE configs (never allowed to break the headline line)."""
   out = {}
-  try:  # config 3: beam_size=30, look_ahead=2 (wide-beam stress), device-resident, 148 x 100 frames
-    from uisrnn_b200.synth import synth_utt
-    U3, N3 = 148, 100
-    x3 = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N3, dim=DIM)[0] for u in range(U3)]).astype(np.float32)).cuda()
-    lab3 = torch.empty(U3 * N3, dtype=torch.int32, device='cuda')
-    off3 = np.arange(U3 + 1, dtype=np.int64) * N3
-    for _ in range(2):
-      model.predict_device(x3.data_ptr(), off3, lab3.data_ptr(), beam_size=30, look_ahead=2, test_iteration=TEST_ITER)
-      st3 = model.stats()
-    out['config3_beam30_lookahead2'] = {'frames_per_s': U3 * N3 / (st3['beam_ms'] / 1e3), 'kernel_ms': st3['beam_ms'],
-                                        'gru_columns_per_step': st3['gru_columns'] / max(1, st3['beam_steps'])}
-  except Exception as err:  # pylint: disable=broad-except
-    out['config3_beam30_lookahead2'] = {'error': str(err)[:200]}
-  try:  # SURVEY 8(d): latency mode (U=1), small batches and the FFMA engine on the bench batch, device-resident
-    from uisrnn_b200.synth import synth_utt
-    for U1, engine in ((1, 0), (64, 0), (296, 1)):
-      xs = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N_FRAMES, dim=DIM)[0] for u in range(U1)]).astype(np.float32)).cuda()
-      lab = torch.empty(U1 * N_FRAMES, dtype=torch.int32, device='cuda')
-      offs = np.arange(U1 + 1, dtype=np.int64) * N_FRAMES
-      for _ in range(2):
-        model.predict_device(xs.data_ptr(), offs, lab.data_ptr(), beam_size=BEAM, look_ahead=LOOK_AHEAD,
-                             test_iteration=TEST_ITER, engine=engine)
-        stu = model.stats()
-      key = 'config2_U%d' % U1 + ('_ffma_engine' if engine == 1 else '')
-      out[key] = {'frames_per_s': U1 * N_FRAMES / ((stu['beam_ms'] + stu['prepass_ms']) / 1e3),
-                  'ms': stu['beam_ms'] + stu['prepass_ms'], 'ctas': stu['ctas'], 'lanes': stu['lanes'],
-                  'cluster': stu['cluster'], 'engine': stu['engine']}
-  except Exception as err:  # pylint: disable=broad-except
-    out['config2_small_batches'] = {'error': str(err)[:200]}
   try:  # config 4: fit() iteration on 50k concatenated frames, batch_size=32 (device trainer, csrc/uis_train.cu)
     import random
     from uisrnn_b200 import native, utils
@@ -233,6 +204,35 @@ def secondary_metrics(model, torch):
     tr.close()
   except Exception as err:  # pylint: disable=broad-except
     out['config4_fit_batch32'] = {'error': str(err)[:200]}
+  try:  # config 3: beam_size=30, look_ahead=2 (wide-beam stress), device-resident, 148 x 100 frames
+    from uisrnn_b200.synth import synth_utt
+    U3, N3 = 148, 100
+    x3 = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N3, dim=DIM)[0] for u in range(U3)]).astype(np.float32)).cuda()
+    lab3 = torch.empty(U3 * N3, dtype=torch.int32, device='cuda')
+    off3 = np.arange(U3 + 1, dtype=np.int64) * N3
+    for _ in range(2):
+      model.predict_device(x3.data_ptr(), off3, lab3.data_ptr(), beam_size=30, look_ahead=2, test_iteration=TEST_ITER)
+      st3 = model.stats()
+    out['config3_beam30_lookahead2'] = {'frames_per_s': U3 * N3 / (st3['beam_ms'] / 1e3), 'kernel_ms': st3['beam_ms'],
+                                        'gru_columns_per_step': st3['gru_columns'] / max(1, st3['beam_steps'])}
+  except Exception as err:  # pylint: disable=broad-except
+    out['config3_beam30_lookahead2'] = {'error': str(err)[:200]}
+  try:  # latency mode (U=1), small batches and the FFMA engine on the bench batch, device-resident
+    from uisrnn_b200.synth import synth_utt
+    for U1, engine in ((1, 0), (64, 0), (296, 1)):
+      xs = torch.from_numpy(np.concatenate([synth_utt(1000 + u, n_frames=N_FRAMES, dim=DIM)[0] for u in range(U1)]).astype(np.float32)).cuda()
+      lab = torch.empty(U1 * N_FRAMES, dtype=torch.int32, device='cuda')
+      offs = np.arange(U1 + 1, dtype=np.int64) * N_FRAMES
+      for _ in range(2):
+        model.predict_device(xs.data_ptr(), offs, lab.data_ptr(), beam_size=BEAM, look_ahead=LOOK_AHEAD,
+                             test_iteration=TEST_ITER, engine=engine)
+        stu = model.stats()
+      key = 'config2_U%d' % U1 + ('_ffma_engine' if engine == 1 else '')
+      out[key] = {'frames_per_s': U1 * N_FRAMES / ((stu['beam_ms'] + stu['prepass_ms']) / 1e3),
+                  'ms': stu['beam_ms'] + stu['prepass_ms'], 'ctas': stu['ctas'], 'lanes': stu['lanes'],
+                  'cluster': stu['cluster'], 'engine': stu['engine']}
+  except Exception as err:  # pylint: disable=broad-except
+    out['config2_small_batches'] = {'error': str(err)[:200]}
   return out
 
 

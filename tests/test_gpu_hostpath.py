@@ -39,7 +39,7 @@ def test_chunked_copies_do_not_change_labels(toy_native, monkeypatch):
   got = toy_native.predict(xs)
   st = toy_native.stats()
   rows = sum(len(x) for x in xs)
-  assert st['chunks'] == -(-rows // 256) and st['chunks'] > 6
+  assert st['chunks'] == -(-rows // 256) and st['chunks'] > 3   # more chunks than staging slots: the ring wraps
   assert st['kernel_launches'] == 1 + 2 * st['chunks']
   for a, b in zip(got, want):
     assert np.array_equal(a, b)

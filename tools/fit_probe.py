@@ -30,9 +30,11 @@ def params(depth):
   return p
 
 
-for depth, batch, barrier, dropout in ((1, 32, 'cg', 0.0), (1, 32, 'spin', 0.0), (1, 64, 'cg', 0.0), (1, 128, 'cg', 0.0),
-                                       (2, 32, 'cg', 0.2), (1, 8, 'cg', 0.0)):
+for depth, batch, barrier, dropout, tiles in ((1, 32, 'cg', 0.0, '128'), (1, 32, 'cg', 0.0, '64'), (1, 32, 'spin', 0.0, '128'),
+                                              (1, 64, 'cg', 0.0, '128'), (1, 128, 'cg', 0.0, '128'), (2, 32, 'cg', 0.2, '128'),
+                                              (1, 8, 'cg', 0.0, '128')):
   os.environ['UISRNN_B200_TRAIN_BARRIER'] = barrier
+  os.environ['UISRNN_B200_TRAIN_GEMM'] = tiles
   hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5, 'grad_max_norm': 5.0,
         'train_sigma2': True, 'rnn_depth': depth, 'rnn_dropout': dropout, 'dropout_seed': 7}
   tr = native.NativeTrainer(params(depth), hp)
@@ -55,7 +57,7 @@ for depth, batch, barrier, dropout in ((1, 32, 'cg', 0.0), (1, 32, 'spin', 0.0),
   e1.record()
   last = tr.losses(1)
   wall = time.perf_counter() - t0
-  print(json.dumps({'depth': depth, 'batch': batch, 'barrier': barrier, 'dropout': dropout, 'iters': iters,
+  print(json.dumps({'depth': depth, 'batch': batch, 'barrier': barrier, 'gemm_tiles': tiles, 'dropout': dropout, 'iters': iters,
                     'wall_ms_per_it': round(1e3 * wall / iters, 3), 'device_ms_per_it': round(e0.elapsed_time(e1) / iters, 3),
                     'host_enqueue_ms_per_it': round(1e3 * host / iters, 3), 'packed_rows_per_s': round(rows / wall),
                     'loss1_last': float(last[0, 0])}), flush=True)

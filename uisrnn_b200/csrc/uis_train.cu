@@ -136,6 +136,117 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
   }
 }
 
+// The same product on 128x128 CTA tiles (BK = 16, 256 threads, 8x8 register micro-tile: rows ty*8.., columns tx*4.. and
+// 64+tx*4..; operands of the inner loop come from shared memory as float4, broadcast over the half-warp for A and
+// contiguous for B): 4x the flops per shared-memory byte of the 64x64 kernel.  Used when both M and N reach 128.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256, 2) gemm128_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                      const float* __restrict__ bias, const float* __restrict__ mask,
+                                                      float* __restrict__ C, int M, int N, int K, int relu,
+                                                      int accumulate, float* __restrict__ partial,
+                                                      unsigned* __restrict__ tickets) {
+  __shared__ __align__(16) float As[16][128 + 4];
+  __shared__ __align__(16) float Bs[16][128 + 4];
+  __shared__ unsigned last_flag;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+  const int splits = gridDim.z;
+  const int kslice = ((K + splits - 1) / splits + 15) / 16 * 16;
+  const int kbeg = blockIdx.z * kslice, kend = min(K, kbeg + kslice);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {  // 128 x 16 elements per operand, 8 per thread, coalesced along the stored-contiguous axis
+      const int q = tid + r * 256;
+      int mm, kk;
+      if (TA) { mm = q % 128; kk = q / 128; } else { kk = q % 16; mm = q / 16; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int q = tid + r * 256;
+      int nn, kk;
+      if (TB) { kk = q % 16; nn = q / 16; } else { nn = q % 128; kk = q / 128; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // element (i, j) of the micro-tile -> tile coordinates
+  auto row_of = [&](int i) { return ty * 8 + i; };
+  auto col_of = [&](int j) { return (j < 4 ? 0 : 64) + tx * 4 + (j & 3); };
+  if (splits > 1) {  // park the partial tile; the last CTA of this tile folds all of them in order
+    const unsigned tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = partial + ((size_t)tile_id * splits + blockIdx.z) * (128 * 128);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      *reinterpret_cast<float4*>(mine + row_of(i) * 128 + col_of(0)) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(mine + row_of(i) * 128 + col_of(4)) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(&tickets[tile_id], 1u);
+      last_flag = (t == (unsigned)splits - 1) ? 1u : 0u;
+      if (last_flag) tickets[tile_id] = 0;
+    }
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    const float* tile = partial + (size_t)tile_id * splits * (128 * 128);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s2 = 0; s2 < splits; ++s2) {
+          const float4 q = *reinterpret_cast<const float4*>(tile + (size_t)s2 * (128 * 128) + row_of(i) * 128 + col_of(4 * h));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        acc[i][4 * h] = v.x; acc[i][4 * h + 1] = v.y; acc[i][4 * h + 2] = v.z; acc[i][4 * h + 3] = v.w;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + row_of(i);
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + col_of(j);
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask) v = (mask[(size_t)gm * N + gn] > 0.f) ? v : 0.f;
+      if (accumulate) v += C[(size_t)gm * N + gn];
+      C[(size_t)gm * N + gn] = v;
+    }
+  }
+}
+
 // column sums: out[n] = sum_r A[r][n]   (one warp per 32 columns, rows strided over the block)
 __global__ void colsum_kernel(const float* __restrict__ A, float* __restrict__ out, int R, int N) {
   __shared__ float part[8][32];
@@ -672,6 +783,12 @@ __global__ void dropout_kernel(const float* __restrict__ in, float* __restrict__
   }
 }
 __global__ void set_scalar_kernel(float* p, float v) { *p = v; }
+// hs_l[b][:] = h0[l][:] for every batch column b and layer l (one launch instead of depth * B small copies)
+__global__ void broadcast_h0_kernel(float* __restrict__ hs, const float* __restrict__ h0, size_t layer_stride, int B, int H) {
+  const int l = blockIdx.y;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < B * H; q += gridDim.x * blockDim.x)
+    hs[(size_t)l * layer_stride + q] = h0[(size_t)l * H + q % H];
+}
 __global__ void cast_rows_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -698,21 +815,29 @@ struct SplitCtx {
   size_t partial_cap = 0;       // floats
   unsigned* tile_tickets = nullptr;
   int ticket_cap = 0;
+  bool force_small = false;     // UISRNN_B200_TRAIN_GEMM=64: the 64x64-tile kernel everywhere (A/B timing)
 };
 
 template <bool TA, bool TB>
 int gemm(cudaStream_t st, const SplitCtx& sc, const float* A, const float* B, const float* bias, const float* mask,
          float* C, int M, int N, int K, bool relu = false, bool acc = false) {
   if (M <= 0 || N <= 0) return 0;
-  dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+  const bool big = M >= 128 && N >= 128 && !sc.force_small;  // 128x128 tiles; tiny models keep the 64x64 kernel
+  const int T = big ? 128 : 64;
+  dim3 grid((N + T - 1) / T, (M + T - 1) / T, 1);
   const int tiles = grid.x * grid.y;
   int splits = 1;
-  // fill the machine (~4 CTAs per SM) when the tile count is small and K is long
-  while (splits < 16 && tiles * splits < 592 && K / (splits * 2) >= 128) splits *= 2;
-  if (splits > 1 && ((size_t)tiles * splits * 4096 > sc.partial_cap || tiles > sc.ticket_cap)) splits = 1;
+  // fill the machine (>= 2 waves of CTAs) when the tile count is small and K is long
+  const int want = big ? 296 : 592;
+  while (splits < 16 && tiles * splits < want && K / (splits * 2) >= 128) splits *= 2;
+  if (splits > 1 && ((size_t)tiles * splits * T * T > sc.partial_cap || tiles > sc.ticket_cap)) splits = 1;
   grid.z = splits;
-  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0, sc.partial,
-                                          sc.tile_tickets);
+  if (big)
+    gemm128_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0, sc.partial,
+                                               sc.tile_tickets);
+  else
+    gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, bias, mask, C, M, N, K, relu ? 1 : 0, acc ? 1 : 0, sc.partial,
+                                            sc.tile_tickets);
   CUT(cudaGetLastError());
   return 0;
 }
@@ -867,8 +992,12 @@ int uis_trainer_create(uis_trainer** out, int device, int D, int H, const float*
     CUT(cudaMemset(t->tickets, 0, 256 * sizeof(unsigned)));
     CUT(cudaMalloc(&t->gemm_tickets, 4096 * sizeof(unsigned)));
     CUT(cudaMemset(t->gemm_tickets, 0, 4096 * sizeof(unsigned)));
-    if (int rc = t->gemm_partial.ensure((size_t)1024 * 4096)) return rc;  // 16 MB of split-K partial tiles
+    if (int rc = t->gemm_partial.ensure((size_t)4096 * 4096)) return rc;  // 64 MB of split-K partial tiles
     t->sc.partial = t->gemm_partial.p; t->sc.partial_cap = t->gemm_partial.cap; t->sc.tile_tickets = t->gemm_tickets; t->sc.ticket_cap = 4096;
+    {
+      const char* env = std::getenv("UISRNN_B200_TRAIN_GEMM");
+      t->sc.force_small = env && std::strcmp(env, "64") == 0;
+    }
     return 0;
   };
   if (int rc = body()) { uis_trainer_destroy(t); return rc; }
@@ -1102,10 +1231,9 @@ int run_iteration(uis_trainer* t, const int32_t* lengths, int B, int L, int mode
   CUT(cudaMemsetAsync(t->dgi.p, 0, R * 3 * H * 4, st));
   CUT(cudaMemsetAsync(t->dgh.p, 0, R * 3 * H * 4, st));
   // h_{-1} of layer l = rnn_init_hidden[l] repeated over the batch (uisrnn.py:262)
-  for (int l = 0; l < depth; ++l)
-    for (int b = 0; b < B; ++b)
-      CUT(cudaMemcpyAsync(t->hs.p + (size_t)l * RB + (size_t)b * H, P + so[t->seg_h0()] + (size_t)l * H, (size_t)H * 4,
-                          cudaMemcpyDeviceToDevice, st));
+  broadcast_h0_kernel<<<dim3((unsigned)std::min<size_t>(((size_t)B * H + 255) / 256, 256), depth), 256, 0, st>>>(
+      t->hs.p, P + so[t->seg_h0()], RB, B, H);
+  CUT(cudaGetLastError());
   if (t->seq_mode < 0) {
     if (int rc = seq_setup(t)) return rc;
   }

@@ -32,8 +32,9 @@ def predict_sharded(model, test_sequences, args, group=None, lengths=None, root=
   if lengths is not None and len(lengths) != len(test_sequences):
     raise ValueError('lengths must have one entry per test sequence.')
   if not (dist.is_available() and dist.is_initialized()):
-    out = model.predict([_materialise(s) for s in test_sequences], args)
-    return [np.asarray(o, dtype=np.int32) for o in out] if as_arrays else out
+    if as_arrays:
+      return _predict_arrays(model, [_materialise(s) for s in test_sequences], args)
+    return model.predict([_materialise(s) for s in test_sequences], args)
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
   lengths = [len(s) for s in test_sequences] if lengths is None else [int(n) for n in lengths]
