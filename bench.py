@@ -694,7 +694,7 @@ def run_b200(args):
                   'uis_predict_wall': e2e_stats['host_ms'], 'h2d_copy_stream_span': e2e_stats['h2d_ms'],
                   'cast_and_input_projection_span_overlapped_with_h2d': e2e_stats['pipeline_ms'],
                   'beam_kernel': e2e_stats['beam_ms'], 'staging_chunks': e2e_stats['chunks'],
-                  'python_and_gather': e2e_ms / args.steps - e2e_stats['host_ms']},
+                  'python_and_gather': max(0.0, e2e_ms / args.steps - e2e_stats['host_ms'])},
               'path': ('uisrnn_b200.distributed.predict_sharded(UISRNN, list, lengths, root=0, as_arrays=True) -> shard_by_frames -> '
                        'uis_predict() per rank -> dist.gather of one int32 label tensor per rank -> int32 arrays on rank 0'
                        if world > 1 else

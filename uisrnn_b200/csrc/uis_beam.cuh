@@ -157,7 +157,7 @@ enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRAC
        LS_NWIN, LS_ERR, LS_M, LS_COLBASE, LS_NE, LS_ROW0_LO, LS_ROW0_HI, LS_DBGROWS_LO, LS_DBGROWS_HI,
        LS_FRESH, LS_COUNT = 24 };
 // CTA scalars
-enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT, MI_NLIST, MI_MAXK };
+enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT, MI_NLIST, MI_MAXK, MI_TCEXIT };
 
 template <int H, int D, int kCP = kCPBeam, bool XCL = false, int TCN = 0>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         mbar_init(&tb.empty[s], 1);
       }
       for (int s = 0; s < kTcSlots; ++s) {
-        mbar_init(&tb.tfull[s], 1);
+        mbar_init(&tb.tfull[s], kTcIssuers);
         mbar_init(&tb.tempty[s], NW);
       }
       mbar_init(tb.bready, NW);
@@ -903,9 +903,10 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     if constexpr (TC) {
       if (warp == NW)
         tc_producer_loop<TCC, H>(&p.tc_wmap, reinterpret_cast<unsigned char*>(ring), tb, &misc[MI_DONE]);
-      else if (warp == NW + 1)  // the whole warp runs the issue loop (uniform operands); one elected lane issues
+      else if (warp == NW + 1 || (kTcIssuers == 2 && warp == NW + 2))  // whole warps run the issue loop (uniform operands); one elected lane issues
         tc_mma_loop<TCC>(reinterpret_cast<const unsigned char*>(ring), reinterpret_cast<const unsigned char*>(XA), tmem_base,
-                         tb, &misc[MI_DONE], reinterpret_cast<long long*>(smem + L.phase) + 16, lane);
+                         tb, &misc[MI_DONE], reinterpret_cast<long long*>(smem + L.phase) + 16, lane, warp - (NW + 1),
+                         &misc[MI_TCEXIT]);
       __syncwarp();
       tc_teardown();
     } else {

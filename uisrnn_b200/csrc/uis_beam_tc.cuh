@@ -30,6 +30,11 @@ namespace uis {
 
 constexpr int kTcBoxBytes = 16384;  // 128 rows x 64 k, fp16
 constexpr int kTcSlots = 5;         // TMEM accumulator slots
+#ifndef UIS_TC_COMMIT_PER_BOX
+constexpr unsigned kTcPairMask = 1u;  // one commit per pair of ring boxes (8 MMAs)
+#else
+constexpr unsigned kTcPairMask = 0u;  // one commit per ring box (4 MMAs): the earlier scheme, kept for A/B builds
+#endif
 
 template <int H, int D, int N>
 struct TcCfg {
@@ -183,7 +188,9 @@ __device__ void tc_producer_loop(const CUtensorMap* wmap, unsigned char* ring, c
       for (int pl = 0; pl < 2 && run; ++pl) {  // plane 0 = lo, 1 = hi
         for (int ka = 0; ka < TC::KA; ++ka, ++it) {
           const unsigned s = it % TC::STAGES, ph = (it / TC::STAGES) & 1;
-          if (!tc_wait_or_done(&b.empty[s], ph ^ 1, done_flag)) { run = false; break; }
+          // ring boxes are released in PAIRS (stages 2j, 2j + 1) by one tcgen05.commit on the odd stage's barrier: the
+          // issuing thread stalls on every commit, so halving their number shortens the pass (tc_mma_loop)
+          if (!tc_wait_or_done(&b.empty[s | kTcPairMask], ph ^ 1, done_flag)) { run = false; break; }
           if (tc_elect_one()) {
             mbar_arrive_expect_tx(&b.full[s], kTcBoxBytes);
             tc_tma_load_2d(ring + (size_t)s * kTcBoxBytes, wmap, ka * 64, pl * TC::ROWS + row0, &b.full[s]);
@@ -205,45 +212,85 @@ __device__ void tc_producer_loop(const CUtensorMap* wmap, unsigned char* ring, c
 // cycles per MMA against ~60 for the MMA itself).  Descriptors are one 64-bit constant plus the 16-byte-unit address.
 // tstat[0..3]: cycles the issuer spent stalled on (0) a ring box not yet landed, (1) an accumulator slot not yet
 // drained by the epilogue warps, (2) the B operand of the next product / the next pass; (3) cycles inside passes
+// Two issuing warps (-DUIS_TC_ISSUERS=2; an experiment that is kept because its result is the argument of DESIGN.md 4.2).
+// Between two bursts of MMAs the issuing thread needs ~300 cycles for the barrier polls, the uniform-register descriptor
+// set-up and the commit, and it cannot run ahead of the tensor pipe; the hypothesis was that this exposed work explains the
+// 128 cycles per MMA of the kernel against the 86-cycle floor of a bare loop.  With two warps taking the box pairs in turn
+// -- role 0 the even pairs of every tile, role 1 the odd ones, a token handed over through two named barriers so that the
+// bursts enter the pipe in the same order, both threads arriving on the accumulator's `tfull` barrier -- the preparation of
+// a pair overlaps the other warp's burst.  Measured on B200 (888 utterances): labels identical, 128.0 ms against 124.1 ms
+// with one issuer, 77 us of issue time per pass against 75: the issue overhead is NOT what holds the pipe back.  What does:
+// every 128 x 96 x 16 MMA moves 4 KB into shared memory (TMA) and 4 KB + 3 KB out of it (A and B operand reads), 11 KB
+// through a 128 B/clk port = 88 cycles before the consumer warps touch shared memory at all.  Default: one issuer.
+#ifndef UIS_TC_ISSUERS
+#define UIS_TC_ISSUERS 1
+#endif
+constexpr int kTcIssuers = UIS_TC_ISSUERS;
+constexpr int kTcTokenBarA = 2, kTcTokenBarB = 3;  // named barriers (0 = __syncthreads, 1 = consumer warps)
+__device__ __forceinline__ void tc_token_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tc_token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 template <class TC>
 __device__ void tc_mma_loop(const unsigned char* ring, const unsigned char* bop, uint32_t tmem_base, const TcBars& b,
-                            volatile int* done_flag, long long* tstat, int lane) {
+                            volatile int* done_flag, long long* tstat, int lane, int role, volatile int* exit_flag) {
   constexpr uint32_t idesc = tc_idesc_f16(TC::NP);
   const uint64_t desc0 = tc_desc_sw128(0);  // every field but the start address
   const uint32_t ring16 = smem_u32(ring) >> 4, bop16 = smem_u32(bop) >> 4;
+  constexpr bool kTwo = kTcIssuers == 2;
+  // token: role 0 issues first; it waits on bar B (role 1's hand-over) before every pair but the very first one
+  const int my_wait = role == 0 ? kTcTokenBarB : kTcTokenBarA, my_give = role == 0 ? kTcTokenBarA : kTcTokenBarB;
+  bool first = true;
   unsigned tc = 0, nb = 0;
   for (;;) {
     for (int t = 0; t < TC::TILES; ++t, ++tc) {
-      if (t == 0 || t == TC::T1 || t == TC::T1 + TC::T2) {  // a new B operand (h_src, h', a) must be in place
-        const long long w0 = clock64();
-        if (!tc_wait_or_done(b.bready, nb & 1, done_flag)) return;
-        const long long w1 = clock64();
-        if (lane == 0) { if (t == 0) tstat[3] -= w1; else tstat[2] += w1 - w0; }
-        ++nb;
-      }
       const unsigned slot = tc % kTcSlots;
-      tc_mbar_wait(&b.tempty[slot], ((tc / kTcSlots) & 1) ^ 1);
+      if (role == 0) {
+        if (t == 0 || t == TC::T1 || t == TC::T1 + TC::T2) {  // a new B operand (h_src, h', a) must be in place
+          const long long w0 = clock64();
+          if (!tc_wait_or_done(b.bready, nb & 1, done_flag)) {
+            if (kTwo) { *exit_flag = 1; __threadfence_block(); tc_token_arrive(my_give); }  // release the other issuer
+            return;
+          }
+          const long long w1 = clock64();
+          if (lane == 0) { if (t == 0) tstat[3] -= w1; else tstat[2] += w1 - w0; }
+          ++nb;
+        }
+        tc_mbar_wait(&b.tempty[slot], ((tc / kTcSlots) & 1) ^ 1);
+      }
       const uint32_t d_tmem = tmem_base + slot * TC::NP;
       const uint32_t tpar = (tc * (unsigned)((2 * TC::KA) / TC::STAGES)) & 1u;  // ring revolutions before this tile
       // One tile = 2 * KA boxes (lo plane, then hi plane), a whole number of ring revolutions, so the ring stage of every
-      // box is a compile-time constant and its barrier parity is one XOR away from one.  Boxes go in pairs -- both waits, eight MMAs back to
-      // back, two commits: every instruction between two MMAs is exposed (the issuing thread cannot run ahead of the
-      // tensor pipe by more than one short MMA), measured 86 cycles per MMA in a bare loop, 130 with per-box overhead.
+      // box is a compile-time constant and its barrier parity is one XOR away from one.  Boxes go in pairs -- both waits,
+      // eight MMAs back to back, one commit for the pair.
 #pragma unroll 1
       for (int q = 0; q < 2 * TC::KA; q += 2) {  // (not unrolled: 16 precomputed descriptor pairs would spill)
+        if (kTwo && ((q >> 1) & 1) != role) continue;
         constexpr int S = TC::STAGES;
         const uint32_t s0 = (uint32_t)q % S, par = tpar ^ (((uint32_t)q / S) & 1u);  // boxes q, q + 1: stages s0, s0 + 1
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (!mbar_try_wait(&b.full[s0 + u], par)) {
-            const long long w0 = clock64();
-            tc_mbar_wait(&b.full[s0 + u], par);
-            if (lane == 0) tstat[0] += clock64() - w0;
+            if (role == 0) {
+              const long long w0 = clock64();
+              tc_mbar_wait(&b.full[s0 + u], par);
+              if (lane == 0) tstat[0] += clock64() - w0;
+            } else {
+              // role 1 runs ahead into the tile after the last pass: those boxes may never be loaded (the producer stops
+              // when the consumer warps announce the end), so this wait gives up with the kernel
+              if (!tc_wait_or_done(&b.full[s0 + u], par, done_flag)) return;
+            }
           }
         }
-        tc_fence_after();
         const uint64_t adesc = desc0 + (uint64_t)(ring16 + s0 * (kTcBoxBytes >> 4));
         const uint64_t bdesc = desc0 + (uint64_t)(bop16 + ((uint32_t)q % TC::KA) * (TC::ATOM_BYTES >> 4));
+        if (kTwo) {
+          if (!first || role == 1) {
+            tc_token_wait(my_wait);  // the previous pair (other warp) has been issued
+            if (role == 1 && *exit_flag) return;
+          }
+          first = false;
+        }
+        tc_fence_after();
         if (tc_elect_one()) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -251,14 +298,15 @@ __device__ void tc_mma_loop(const unsigned char* ring, const unsigned char* bop,
             for (int kk = 0; kk < 4; ++kk)  // 4 k-steps of 16 inside the 64-wide swizzle atom: +32 bytes = +2 units each
               tc_mma_f16(d_tmem, adesc + (uint64_t)(u * (kTcBoxBytes >> 4) + 2 * kk),
                          bdesc + (uint64_t)(u * (TC::ATOM_BYTES >> 4) + 2 * kk), idesc, (q | u | kk) != 0);
-            tc_commit(&b.empty[s0 + u]);  // frees the ring box when the MMAs above have read it
+            if (u == 1 || !kTcPairMask) tc_commit(&b.empty[s0 + u]);  // frees the ring boxes when the MMAs above have read them
           }
-          if (q == 2 * TC::KA - 2) tc_commit(&b.tfull[slot]);
+          if (q >= 2 * TC::KA - (kTwo ? 4 : 2)) tc_commit(&b.tfull[slot]);  // this thread's last burst of the tile
         }
         __syncwarp();
+        if (kTwo) tc_token_arrive(my_give);
       }
     }
-    if (lane == 0) tstat[3] += clock64();  // issue time of the pass (first B operand ready -> last MMA issued)
+    if (lane == 0 && role == 0) tstat[3] += clock64();  // issue time of the pass (first B operand ready -> last MMA issued)
   }
 }
 
