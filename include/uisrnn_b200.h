@@ -43,11 +43,12 @@ typedef struct uis_model uis_model; /* opaque */
 
 /* Inference options = the reference's inference_args (uisrnn/arguments.py:172-193). */
 typedef struct uis_predict_opts {
-  int32_t beam_size;      /* --beam_size      (arguments.py:175-180), >= 1                     */
+  int32_t beam_size;      /* --beam_size      (arguments.py:175-180), 1..128 (1..32 when look_ahead >= 2) */
   int32_t look_ahead;     /* --look_ahead     (arguments.py:181-185), >= 1                     */
   int32_t test_iteration; /* --test_iteration (arguments.py:186-193), >= 1                     */
   int32_t kcap;           /* max clusters per hypothesis held on device; 0 = default (32; 16
-                             when look_ahead >= 2)                                             */
+                             when look_ahead >= 2 or on the tensor-core engine; beam_size > 32:
+                             the largest of 32, 16, 8, 4 whose tables fit shared memory)        */
   int32_t n_ctas;         /* persistent CTAs to launch; 0 = one per SM                         */
   int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
                              0 = auto (FFMA engine: 2 when U >= 2 * CTAs, else 1, max 4;

@@ -57,7 +57,7 @@ def test_unsupported_configurations_raise_instead_of_falling_back():
   case = [c for c in small_cases() if c['name'] == 'la2'][0]
   assert small.predict(case['x'], inference_args(5, 2, 1)) == case['labels'].tolist()   # look_ahead 2 kernel
   with pytest.raises(native.NativeError) as ei:
-    small.predict(case['x'], inference_args(40, 1, 1))           # beam > 32: no kernel
+    small.predict(case['x'], inference_args(200, 1, 1))          # beam > 128: no kernel
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   import uisrnn
   m, _, _ = uisrnn.parse_arguments([])

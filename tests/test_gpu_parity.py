@@ -142,7 +142,10 @@ def test_unsupported_options_fail_loudly(small_model, native):
     small_model.predict([x], look_ahead=9)
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   with pytest.raises(native.NativeError) as ei:
-    small_model.predict([x], beam_size=33)
+    small_model.predict([x], beam_size=129)                  # look_ahead 1 serves beam_size <= 128
+  assert ei.value.code == native.UIS_ERR_UNSUPPORTED
+  with pytest.raises(native.NativeError) as ei:
+    small_model.predict([x], beam_size=33, look_ahead=2)     # the look-ahead tree kernel: beam_size <= 32
   assert ei.value.code == native.UIS_ERR_UNSUPPORTED
   with pytest.raises(native.NativeError):
     small_model.predict([x], beam_size=0)
@@ -158,6 +161,34 @@ def test_look_ahead_fresh_inputs_match_oracle(small_model, beam, la, titer):
   for x, o in zip(xs, got):
     want = uis_oracle.predict_single(om, x, beam_size=beam, look_ahead=la, test_iteration=titer)
     assert o.tolist() == want
+
+
+@pytest.mark.parametrize('beam,engine', [(33, 1), (40, 0), (64, 1), (100, 1), (128, 0)])
+def test_beams_wider_than_32_match_oracle(small_model, beam, engine):
+  """beam_size > 32 (any int in the reference, arguments.py:175-180): phase P3 walks the winners in chunks of 32 and
+  the candidate records carry a 7-bit hypothesis index.  Labels against the oracle; a hand-picked kcap keeps the
+  per-hypothesis tables (B * kcap entries) inside shared memory."""
+  from uisrnn_b200.synth import synth_utt
+  om = oracle_model('model_small.npz')
+  xs = [synth_utt(9700 + i, n_frames=n, dim=64, n_spk=k, noise=0.08)[0]
+        for i, (n, k) in enumerate([(40, 3), (1, 1), (23, 2), (57, 4)])]
+  got = small_model.predict(xs, beam_size=beam, look_ahead=1, test_iteration=2, engine=engine)
+  st = small_model.stats()
+  assert st['engine'] == (engine or st['engine'])
+  for x, o in zip(xs, got):
+    assert o.tolist() == uis_oracle.predict_single(om, x, beam_size=beam, look_ahead=1, test_iteration=2)
+
+
+@pytest.mark.parametrize('engine', [1, 2])
+def test_beam_64_default_shape_matches_oracle(toy_model, engine):
+  """Both engines at the default shape; on the tensor-core engine a lane's columns (up to 65) span two passes."""
+  from uisrnn_b200.synth import synth_utt
+  om = oracle_model('model_toy100.npz')
+  xs = [synth_utt(4321 + i, n_frames=30)[0] for i in range(3)]
+  got = toy_model.predict(xs, beam_size=64, look_ahead=1, test_iteration=2, engine=engine)
+  assert toy_model.stats()['engine'] == engine
+  for x, o in zip(xs, got):
+    assert o.tolist() == uis_oracle.predict_single(om, x, beam_size=64, look_ahead=1, test_iteration=2)
 
 
 def test_wide_beam_look_ahead_config3_shape(toy_model):

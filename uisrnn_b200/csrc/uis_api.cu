@@ -309,15 +309,19 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   if (o->beam_size < 1 || o->look_ahead < 1 || o->test_iteration < 1)
     return fail(UIS_ERR_INVALID, "beam_size, look_ahead and test_iteration must be >= 1");
   if (o->look_ahead > 8) return fail(UIS_ERR_UNSUPPORTED, "look_ahead=%d > 8 not supported", o->look_ahead);
-  if (o->beam_size > 32) return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > 32 not supported", o->beam_size);
+  if (o->beam_size > uis::kMaxBeam) return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > %d not supported", o->beam_size, uis::kMaxBeam);
+  if (o->beam_size > 32 && o->look_ahead > 1)
+    return fail(UIS_ERR_UNSUPPORTED, "beam_size=%d > 32 is supported with look_ahead 1 only (look_ahead=%d)", o->beam_size, o->look_ahead);
   if (o->engine < 0 || o->engine > 2) return fail(UIS_ERR_INVALID, "engine must be 0 (auto), 1 (FFMA) or 2 (tensor cores)");
   pl->B = o->beam_size;
   pl->L = o->look_ahead;
   pl->T = o->test_iteration;
   const bool tree = pl->L > 1;
   pl->Kcap = o->kcap > 0 ? o->kcap : (tree ? 16 : 32);
+  if (o->kcap <= 0 && pl->B > 32)  // wide beams: the per-hypothesis tables (B * kcap entries) must fit shared memory
+    while (pl->Kcap > 4 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, 1) > 227u * 1024u) pl->Kcap /= 2;
   pl->tcn = 0;
-  if (pl->Kcap > 2047 || pl->B * pl->Kcap + pl->B + 1 > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
+  if (pl->Kcap > (pl->B > 32 ? 511 : 2047) || pl->B * pl->Kcap + pl->B + 1 > 65535) return fail(UIS_ERR_INVALID, "kcap too large");
   if (tree && pl->Kcap > 255) return fail(UIS_ERR_UNSUPPORTED, "look_ahead >= 2 supports kcap <= 255");
   pl->P = pl->B * pl->Kcap + pl->B + 1;
   pl->rows = U > 0 ? off[U] : 0;
@@ -365,7 +369,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
         int Gt = o->lanes > 0 ? std::min(o->lanes, (int)uis::kMaxLanes)
                               : (int)std::min<long long>(N / 8, ((long long)U + ctas - 1) / std::max(ctas, 1));
         Gt = std::max(Gt, 1);
-        while (Gt > 1 && uis::beam_tc_smem(m->H, m->D, N, pl->B, kc, Gt) > 227u * 1024u) --Gt;
+        while (Gt > 1 && (uis::beam_tc_smem(m->H, m->D, N, pl->B, kc, Gt) > 227u * 1024u || Gt * pl->B > 256)) --Gt;
         const bool fits = uis::beam_tc_smem(m->H, m->D, N, pl->B, kc, Gt) <= 227u * 1024u &&
                           pl->B * kc + pl->B + 1 <= 65535;
         if (fits && (o->engine == 2 || (long long)U > ctas)) {
@@ -384,6 +388,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
     }
     if (!pl->tcn)
       while (G > 1 && smem_bytes(m->H, m->D, pl->B, pl->Kcap, G) > 227u * 1024u) --G;
+    while (G > 1 && G * pl->B > 256) --G;  // phase P4 gives one consumer thread to every (lane, winner)
   }
   if (tree && o->engine == 2) return fail(UIS_ERR_UNSUPPORTED, "tensor-core engine: look_ahead must be 1");
   pl->G = G;
@@ -889,8 +894,26 @@ size_t staging_chunk_rows(int d_user) {
 
 // One group of utterances, host buffers in, host buffers out: chunked H2D on the copy stream || cast + input
 // projection on `st`, then the beam kernel, then one D2H copy of all labels.
+int predict_host_group_impl(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const int64_t* off,
+                            const Plan& pl, int32_t* const* labels_out, const uis_debug_taps* taps, cudaStream_t st);
+
 int predict_host_group(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const int64_t* off,
                        const Plan& pl, int32_t* const* labels_out, const uis_debug_taps* taps, cudaStream_t st) {
+  const int rc = predict_host_group_impl(m, seqs, n_frames, U, off, pl, labels_out, taps, st);
+  if (rc != 0 && rc != UIS_ERR_OVERFLOW && rc != UIS_ERR_CAPACITY) {
+    // a failed call may leave copies / kernels in flight on either stream: drain them (the error already recorded in
+    // uis_last_error() is the one reported) so that the staging ring and the workspace are quiescent for the next call
+    const std::string keep = g_err;
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+    cudaStreamSynchronize(st);
+    (void)cudaGetLastError();
+    g_err = keep;
+  }
+  return rc;
+}
+
+int predict_host_group_impl(uis_model* m, const double* const* seqs, const int64_t* n_frames, int U, const int64_t* off,
+                            const Plan& pl, int32_t* const* labels_out, const uis_debug_taps* taps, cudaStream_t st) {
   const int D = m->D_user, H = m->H;  // the caller's rows; the device rows are padded to m->D floats
   const size_t rows = (size_t)pl.rows;
   if (rows == 0) {

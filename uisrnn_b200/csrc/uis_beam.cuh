@@ -45,6 +45,7 @@ constexpr int kCPCluster = 12;          // cluster (latency) mode: one lane per 
 constexpr int kXchVals = 24;            // floats per thread and exchange round of the cluster K-split
 constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
 constexpr int kMaxLanes = 8;
+constexpr int kMaxBeam = 128;  // beam_size served by the look_ahead-1 kernels (phase P3 walks the winners in chunks of 32)
 constexpr int kMaxDepth = 4;             // stacked GRU layers supported on device
 
 struct TabEntry {
@@ -927,6 +928,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
   unsigned* bp_cta = p.bp + (size_t)blockIdx.x * G * p.maxN * B;
   const unsigned PW = (unsigned)(p.P + 31) / 32;
   const float INF = __int_as_float(0x7f800000);
+  const int bbits = B > 32 ? 7 : 5;  // bits of the hypothesis index inside a candidate record (phase P1)
 
   float bh[C::RG], b1r[UPT];
 #pragma unroll
@@ -1197,7 +1199,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
           pen = (p.log_p0 + p.log_alpha) - __ldg(p.logtot + mTot[b]);
         }
         reinterpret_cast<double*>(lane_base(g) + L.l_keys)[e] = pen;
-        reinterpret_cast<unsigned*>(lane_base(g) + L.l_svals)[e] = (unsigned)slot | ((unsigned)b << 16) | ((unsigned)c << 21);
+        // slot (16 bits) | hypothesis (5 bits, or 7 when beam_size > 32: the host then caps kcap at 511) | cluster
+        reinterpret_cast<unsigned*>(lane_base(g) + L.l_svals)[e] = (unsigned)slot | ((unsigned)b << 16) | ((unsigned)c << (16 + bbits));
       }
       named_bar_sync(1, NT);
       // P1s: the live slots that still lack their term against x_t
@@ -1209,7 +1212,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         while (e >= ne_g[g]) { e -= ne_g[g]; ++g; }
         volatile int* ls = LSp(g);
         const unsigned info = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_svals)[e];
-        const int b = (int)((info >> 16) & 31u), c = (int)(info >> 21);
+        const int b = (int)((info >> 16) & ((1u << bbits) - 1u)), c = (int)(info >> (16 + bbits));
         const float mse = pool_mse_cta[(size_t)g * p.P + (info & 0xffffu)];
         const float* mNl = reinterpret_cast<const float*>(lane_base(g) + L.l_meta) + ls[LS_GEN] * 4 * B + 3 * B;
         const double pen = reinterpret_cast<const double*>(lane_base(g) + L.l_keys)[e];
@@ -1255,7 +1258,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       const int g = warp;
       volatile int* ls = LSp(g);
       const int nwin = ls[LS_NWIN];
-      if (ls[LS_ACTIVE] && nwin > 0) {  // (beam_size <= 32 is enforced by the host)
+      if (ls[LS_ACTIVE] && nwin > 0) {
         const int gen = ls[LS_GEN];
         const int* mK = reinterpret_cast<const int*>(lane_base(g) + L.l_meta) + gen * 4 * B;
         const TabEntry* tab = reinterpret_cast<const TabEntry*>(lane_base(g) + L.l_tabs) + (size_t)gen * B * Kcap;
@@ -1264,24 +1267,56 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         int* lcolsrc = reinterpret_cast<int*>(lane_base(g) + L.l_lcol);
         int* lcolnew = lcolsrc + B;
         const unsigned* used = reinterpret_cast<const unsigned*>(lane_base(g) + L.l_used);
-        const int r = lane;
-        int src = -1;
-        if (r < nwin) {
-          const int b = wins[r], c = wins[B + r];
-          src = (c < mK[b]) ? tab[(size_t)b * Kcap + c].slot : kInitSlot;
+        int M = 0;
+        if (nwin <= 32) {  // one winner per lane (beam_size <= 32, or fewer finite candidates)
+          const int r = lane;
+          int src = -1;
+          if (r < nwin) {
+            const int b = wins[r], c = wins[B + r];
+            src = (c < mK[b]) ? tab[(size_t)b * Kcap + c].slot : kInitSlot;
+          }
+          int first = r;
+          for (int q = 0; q < nwin; ++q) {
+            const int sq = __shfl_sync(0xffffffffu, src, q);
+            if (q < first && sq == src) first = q;
+          }
+          const bool isfirst = (r < nwin) && (first == r);
+          const unsigned fm = __ballot_sync(0xffffffffu, isfirst);
+          const int mycol = __popc(fm & ((1u << lane) - 1));
+          M = __popc(fm);
+          const int c_of_first = __shfl_sync(0xffffffffu, mycol, first);
+          if (r < nwin) wcol[r] = c_of_first;
+          if (isfirst) lcolsrc[mycol] = src;
+        } else {
+          // beam_size > 32: the winners are walked in chunks of 32; their source slots are parked in lcolnew (rewritten
+          // by the slot allocation below) so that every winner can look for an earlier winner with the same source
+          for (int r = lane; r < nwin; r += 32) {
+            const int b = wins[r], c = wins[B + r];
+            lcolnew[r] = (c < mK[b]) ? tab[(size_t)b * Kcap + c].slot : kInitSlot;
+          }
+          __syncwarp();
+          for (int r0 = 0; r0 < nwin; r0 += 32) {  // columns are numbered in winner order, as in the one-chunk case
+            const int r = r0 + lane;
+            int first = r, src = -1;
+            if (r < nwin) {
+              src = lcolnew[r];
+              for (int q = 0; q < r; ++q)
+                if (lcolnew[q] == src) { first = q; break; }
+            }
+            const bool isfirst = (r < nwin) && (first == r);
+            const unsigned fm = __ballot_sync(0xffffffffu, isfirst);
+            if (isfirst) {
+              const int mycol = M + __popc(fm & ((1u << lane) - 1));
+              wcol[r] = mycol;
+              lcolsrc[mycol] = src;
+            }
+            M += __popc(fm);
+            __syncwarp();
+            if (r < nwin && !isfirst) wcol[r] = wcol[first];  // `first` is an earlier winner: its column is already there
+            __syncwarp();
+          }
+          __syncwarp();
         }
-        int first = r;
-        for (int q = 0; q < nwin; ++q) {
-          const int sq = __shfl_sync(0xffffffffu, src, q);
-          if (q < first && sq == src) first = q;
-        }
-        const bool isfirst = (r < nwin) && (first == r);
-        const unsigned fm = __ballot_sync(0xffffffffu, isfirst);
-        const int mycol = __popc(fm & ((1u << lane) - 1));
-        const int M = __popc(fm);
-        const int c_of_first = __shfl_sync(0xffffffffu, mycol, first);
-        if (r < nwin) wcol[r] = c_of_first;
-        if (isfirst) lcolsrc[mycol] = src;
         // allocate M free slots from the bitmap (any free slot will do)
         int cnt = 0;
         for (unsigned w = lane; w < PW; w += 32) {
