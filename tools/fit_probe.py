@@ -30,9 +30,12 @@ def params(depth):
   return p
 
 
-for depth, batch, barrier, dropout, tiles in ((1, 32, 'cg', 0.0, '128'), (1, 32, 'cg', 0.0, '64'), (1, 32, 'spin', 0.0, '128'),
-                                              (1, 64, 'cg', 0.0, '128'), (1, 128, 'cg', 0.0, '128'), (2, 32, 'cg', 0.2, '128'),
-                                              (1, 8, 'cg', 0.0, '128')):
+CASES = ((1, 32, 'cg', 0.0, '128'), (1, 32, 'cg', 0.0, '64'), (1, 32, 'spin', 0.0, '128'), (1, 64, 'cg', 0.0, '128'),
+         (1, 128, 'cg', 0.0, '128'), (2, 32, 'cg', 0.2, '128'), (1, 8, 'cg', 0.0, '128'), (1, 8, 'cg', 0.0, '64'),
+         (1, 10, 'cg', 0.0, '128'), (1, 10, 'cg', 0.0, '64'), (1, 16, 'cg', 0.0, '128'), (1, 16, 'cg', 0.0, '64'))
+if len(sys.argv) > 2 and sys.argv[2] == 'small':
+  CASES = CASES[6:]
+for depth, batch, barrier, dropout, tiles in CASES:
   os.environ['UISRNN_B200_TRAIN_BARRIER'] = barrier
   os.environ['UISRNN_B200_TRAIN_GEMM'] = tiles
   hp = {'learning_rate': 1e-3, 'sigma_alpha': 1.0, 'sigma_beta': 1.0, 'regularization_weight': 1e-5, 'grad_max_norm': 5.0,
