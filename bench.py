@@ -114,8 +114,8 @@ def load_peaks():
 
 def measured_traffic(utts, engine):
   """DRAM bytes per launch of the beam kernel from the committed ncu capture of THIS build's kernel on THIS
-  workload size (profiles/r2_traffic.json); None when the capture does not match what was just run."""
-  path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+  workload size (profiles/r3_traffic.json); None when the capture does not match what was just run."""
+  path = os.path.join(ROOT, 'profiles', 'r3_traffic.json')
   try:
     with open(path) as f:
       d = json.load(f)
@@ -428,7 +428,7 @@ def run_reference(args):
   # Slice length: as long as the time budget allows (the reference needs ~0.1-0.3 s per frame and process).  One
   # calibration step with 16-frame slices on every process, then frames = 16 * budget / t16 (cost is ~linear in the
   # slice length once the beam is full), capped at the workload's 500.
-  budget_total = float(os.environ.get('UIS_BENCH_REF_SECONDS', '600'))
+  budget_total = float(os.environ.get('UIS_BENCH_REF_SECONDS', '420'))
   budget_step = budget_total / max(1, args.steps + args.warmup)
   ctx = mp.get_context('spawn')
   times = []
@@ -646,7 +646,7 @@ def run_b200(args):
               'frac': hbm_alg / beam_s / 1e9 / peaks['hbm_gbs'], 'traffic': traffic,
               'note': 'SURVEY 8(d): weights once per beam step + per-frame I/O; the weights stay L2-resident, so this is not '
                       'the binding resource (traffic = ncu dram bytes of the committed capture of this kernel and batch size, '
-                      'profiles/r2_traffic.json; null if none matches)'},
+                      'profiles/r3_traffic.json; null if none matches)'},
       'l2_to_sm_bytes': st['weight_passes'] * wbytes_pass,
       'fp32_fma_equivalent': {'achieved_tflops': flops / beam_s / 1e12, 'peak_tflops': fp32_peak,
                               'frac': flops / beam_s / 1e12 / fp32_peak, 'sm_mhz_used': sm_mhz,
