@@ -53,9 +53,11 @@ typedef struct uis_predict_opts {
   int32_t lanes;          /* utterances advanced together per CTA (share each weight pass);
                              0 = auto (FFMA engine: 2 when U >= 2 * CTAs, else 1, max 4;
                              tensor-core engine: up to columns / 8 = 6, max 8)                  */
-  int32_t cluster;        /* CTAs per utterance (thread-block cluster, latency mode for few
-                             utterances; default shape, depth 1, look_ahead 1): 0 = auto (4 or 2
-                             when U * cluster <= CTAs), -1 = off, 2 / 4 / 8 = forced               */
+  int32_t cluster;        /* CTAs per utterance (latency modes for few utterances; default shape,
+                             depth 1, look_ahead 1): 0 = auto (32 when U * 32 <= CTAs, else 4 or 2 when
+                             U * cluster <= CTAs), -1 = off, 2 / 4 / 8 = thread-block cluster (k-split of the
+                             streamed weights), 32 = stationary-weights group (weights resident in the
+                             shared memory of 32 CTAs, products split by rows, cooperative launch)         */
   int32_t engine;         /* matrix engine of the look_ahead-1 beam kernel: 0 = auto (tensor cores
                              when some CTA gets more than one utterance), 1 = fp32 FFMA kernels,
                              2 = tcgen05 tensor-core pass (fp16 hi/lo split operands, fp32-grade;
@@ -93,7 +95,7 @@ typedef struct uis_stats {
   float prepass_ms;        /* device time of the input-projection GEMM (CUDA events on `stream`) */
   float beam_ms;           /* device time of the persistent beam-search kernel                 */
   int32_t lanes;           /* lanes per CTA used                                               */
-  int32_t cluster;   /* thread-block cluster size the last call used (1 = none) */
+  int32_t cluster;   /* CTAs per utterance the last call used: 1 = none, 2/4/8 = cluster, 32 = stationary-weights group */
   int32_t engine;          /* 1 = FFMA kernels, 2 = tensor-core pass                            */
   int32_t tc_columns;      /* tensor-core pass: columns per weight pass (0 otherwise)           */
   int64_t phase_cycles[10]; /* SM cycles summed over CTAs: [0] re-pack (P4), [1] gather, [2] GRU pass,

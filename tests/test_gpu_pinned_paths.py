@@ -7,6 +7,7 @@ Variants are forced through the C ABI's `lanes` / `cluster` options (`include/ui
   lanes=2 cluster=-1   uis_beam_kernel<H,D,false,false>, two utterances per CTA sharing each weight pass (bench path)
   lanes=1 cluster=-1   the same kernel, one utterance per CTA
   lanes=0 cluster=0    automatic choice (few utterances -> thread-block-cluster kernel)
+  lanes=0 cluster=32   stationary-weights mode (groups of 32 CTAs, weights resident in shared memory)
   engine=2             the tensor-core pass (tcgen05): tests/test_gpu_tensorcore.py
 """
 import numpy as np
@@ -17,7 +18,7 @@ from helpers import GOLDEN, load_weights, uis_oracle
 pytestmark = pytest.mark.gpu
 
 VARIANTS = [dict(lanes=2, cluster=-1, engine=1), dict(lanes=1, cluster=-1, engine=1), dict(lanes=0, cluster=0, engine=1),
-            dict(lanes=4, cluster=-1, engine=1)]
+            dict(lanes=4, cluster=-1, engine=1), dict(lanes=0, cluster=32, engine=0)]
 
 
 @pytest.fixture(scope='module')

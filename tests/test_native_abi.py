@@ -81,7 +81,7 @@ def test_sass_uses_tcgen05_tmem_and_tensor_map_tma():
     pytest.skip('cuobjdump not available')
   from uisrnn_b200 import native
   sass = subprocess.run([tool, '-sass', native.LIB_PATH], capture_output=True, text=True).stdout
-  start = sass.find('uis_beam_kernelILi512ELi256ELb0ELb0ELi48EE')
+  start = sass.find('uis_beam_kernelILi512ELi256ELb0ELi0ELi48EE')
   assert start >= 0, 'tensor-core instantiation missing'
   end = sass.find('Function :', start + 10)
   body = sass[start:end if end > 0 else len(sass)]

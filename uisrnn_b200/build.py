@@ -15,9 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libuisrnn_b200.so')
 STAMP = LIB + '.srchash'
-SOURCES = ['uis_api.cu', 'uis_train.cu', 'uis_kernels_beam_large.cu', 'uis_kernels_beam_small.cu', 'uis_kernels_beam_cluster.cu', 'uis_kernels_beam_tc.cu',
+SOURCES = ['uis_api.cu', 'uis_train.cu', 'uis_kernels_beam_large.cu', 'uis_kernels_beam_small.cu', 'uis_kernels_beam_cluster.cu', 'uis_kernels_beam_stat.cu', 'uis_kernels_beam_tc.cu',
            'uis_kernels_tree_large.cu', 'uis_kernels_tree_small.cu']
-DEPS = SOURCES + ['uis_beam.cuh', 'uis_beam_tc.cuh', 'uis_beam_tree.cuh', 'uis_prepass.cuh', 'uis_common.cuh', 'uis_launch.cuh',
+DEPS = SOURCES + ['uis_beam.cuh', 'uis_beam_tc.cuh', 'uis_beam_stat.cuh', 'uis_beam_tree.cuh', 'uis_prepass.cuh', 'uis_common.cuh', 'uis_launch.cuh',
         os.path.join('..', '..', 'include', 'uisrnn_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC', '--threads', '0']

@@ -92,7 +92,7 @@ struct uis_model {
   DevBuf wih_t, whh_t, w1_t, w2_t, bih, bhh, b1, b2, wvec, mean0, hidden0;
   DevBuf wih_up_t;  // [depth-1][H][3H]; whh_t is [depth][H][3H]; bih / bhh are [depth][3H]
   // tensor-core pass (uis_beam_tc.cuh): fp16 hi/lo planes of [W_hh; W1; W2] behind a tensor map, scales
-  DevBuf tc_planes, tc_scratch;
+  DevBuf tc_planes, tc_scratch, stat_bar, stat_scratch;
   alignas(64) CUtensorMap tc_map;
   bool tc_ready = false;
   float tc_sh = 0, tc_sa = 0, tc_inv_hh = 0, tc_inv_1 = 0, tc_inv_2 = 0;
@@ -297,6 +297,7 @@ int ensure_log_tables(uis_model* m, int max_tn) {
 struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
   int cluster = 1;  // CTAs per utterance (thread-block cluster size); 1 = one CTA per lane group
+  int stat = 0;     // > 0: stationary-weights mode with this many groups of 32 CTAs (uis_beam_stat.cuh)
   int tcn = 0;      // > 0: tensor-core beam kernel with this many columns per pass (uis_beam_tc.cuh)
   bool cluster_forced = false;
   int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
@@ -398,6 +399,30 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
   // that still gives every utterance its own cluster), -1 = off, 2/4/8 = forced; UISRNN_B200_CLUSTER=0 disables
   // the automatic choice.
   pl->cluster = 1;
+  pl->stat = 0;
+  // Stationary-weights mode (uis_beam_stat.cuh): 32 CTAs per utterance keep the weights in shared memory.  The fastest
+  // way to decode up to #SMs / 32 utterances at a time; opts->cluster = 32 forces it, 0 picks it automatically,
+  // UISRNN_B200_STAT=0 disables the automatic choice.
+  if (!tree && U >= 1 && (o->cluster == 0 || o->cluster == uis::kStatGroup) && !has_taps && m->depth == 1 &&
+      o->lanes <= 1 && o->engine != 2) {
+    const char* env = std::getenv("UISRNN_B200_STAT");
+    const bool want = o->cluster == uis::kStatGroup ||
+                      (!(env && env[0] == '0') && (long long)U * uis::kStatGroup <= ctas && o->engine == 0 && o->n_ctas <= 0);
+    const int kc = o->kcap > 0 ? o->kcap : 32;
+    const bool can = ctas >= uis::kStatGroup && uis::beam_stat_smem(m->H, m->D, pl->B, kc) <= 227u * 1024u &&
+                     pl->B * kc + pl->B + 1 <= 65535;
+    if (want && can) {
+      pl->stat = std::max(1, std::min(ctas / uis::kStatGroup, U));
+      pl->tcn = 0;
+      pl->Kcap = kc;
+      pl->P = pl->B * kc + pl->B + 1;
+      pl->G = 1;
+      pl->ctas = pl->stat * uis::kStatGroup;
+      return 0;
+    }
+    if (o->cluster == uis::kStatGroup)
+      return fail(UIS_ERR_UNSUPPORTED, "stationary-weights mode needs hidden=512 dim=256 depth=1, >= 32 CTAs and beam_size/kcap that fit in shared memory");
+  }
   if (!tree && !pl->tcn && U >= 1 && o->cluster >= 0 && !has_taps && m->depth == 1 && o->lanes <= 1) {
     int cs = 0;
     if (o->cluster == 2 || o->cluster == 4 || o->cluster == 8) {
@@ -408,7 +433,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
         for (int c : {4, 2})
           if ((long long)U * c <= ctas) { cs = c; break; }
     } else {
-      return fail(UIS_ERR_INVALID, "cluster must be -1, 0, 2, 4 or 8");
+      return fail(UIS_ERR_INVALID, "cluster must be -1, 0, 2, 4, 8 or 32");
     }
     if (cs > 1 && uis::beam_cluster_smem(m->H, m->D, pl->B, pl->Kcap) <= 227u * 1024u) {
       const int clusters = std::max(1, std::min(ctas / cs, U));
@@ -473,6 +498,11 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
 
   if (pl.tcn)
     if (int rc = m->tc_scratch.ensure((size_t)pl.ctas * pl.tcn * H * sizeof(float))) return rc;
+  if (pl.stat) {
+    if (int rc = m->stat_bar.ensure((size_t)pl.stat * uis::kStatGroup * sizeof(unsigned))) return rc;
+    if (int rc = m->stat_scratch.ensure((size_t)pl.stat * uis::kCPCluster * H * sizeof(float))) return rc;
+    CU(cudaMemsetAsync(m->stat_bar.p, 0, (size_t)pl.stat * uis::kStatGroup * sizeof(unsigned), st));
+  }
 
   CU(cudaMemcpyAsync(m->row_off.p, off_ll.data(), (U + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(m->order.p, order.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -505,6 +535,10 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   p.stats = m->queue_stats.as<unsigned long long>() + 8;
   p.labels = labels_dev; p.status = m->status.as<int>();
   p.trace_utt = -1;
+  if (pl.stat) {
+    p.stat_bar = m->stat_bar.as<unsigned>();
+    p.stat_scratch = m->stat_scratch.as<float>();
+  }
   if (pl.tcn) {
     p.tc_wmap = m->tc_map;
     p.tc_sh = m->tc_sh; p.tc_sa = m->tc_sa;
@@ -554,7 +588,17 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   CU(cudaEventRecord(m->ev[1], st));
   // kernel 2: persistent beam search
   int cluster_used = pl.cluster;
-  if (pl.tcn) {
+  bool stat_done = false;
+  if (pl.stat) {
+    cudaError_t e = cudaSuccess;
+    const bool have = uis::launch_beam_stat(H, D, p, pl.ctas, uis::beam_stat_smem(H, D, pl.B, pl.Kcap), st, &e);
+    if (!have) return fail(UIS_ERR_UNSUPPORTED, "no stationary-weights kernel for hidden=%d dim=%d", H, D);
+    if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "stationary-weights beam kernel launch failed: %s", cudaGetErrorString(e));
+    cluster_used = uis::kStatGroup;
+    stat_done = true;
+  }
+  if (stat_done) {
+  } else if (pl.tcn) {
     cudaError_t e = cudaSuccess;
     if (!uis::launch_beam_tc(H, D, pl.tcn, p, pl.ctas, uis::beam_tc_smem(H, D, pl.tcn, pl.B, pl.Kcap, pl.G), st, &e))
       return fail(UIS_ERR_UNSUPPORTED, "no tensor-core kernel for hidden=%d dim=%d columns=%d", H, D, pl.tcn);
@@ -813,7 +857,7 @@ int uis_model_destroy(uis_model* m) {
                     &m->hidden0, &m->wih_up_t, &m->logn, &m->logtot, &m->x64, &m->x32, &m->gi, &m->row_off, &m->order,
                     &m->pool_mean, &m->pool_hidden, &m->bp, &m->queue_stats, &m->labels, &m->status, &m->dbg_win,
                     &m->dbg_score, &m->dbg_off, &m->dbg_final_scores, &m->dbg_final_k, &m->dbg_best_mean,
-                    &m->dbg_best_hidden, &m->dbg_best_blocks, &m->tc_planes, &m->tc_scratch, &m->pool_mse};
+                    &m->dbg_best_hidden, &m->dbg_best_blocks, &m->tc_planes, &m->tc_scratch, &m->pool_mse, &m->stat_bar, &m->stat_scratch};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : m->ev)
     if (e) cudaEventDestroy(e);

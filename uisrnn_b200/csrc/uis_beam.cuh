@@ -31,6 +31,7 @@
 #pragma once
 #include "uis_common.cuh"
 #include "uis_beam_tc.cuh"
+#include "uis_beam_stat.cuh"
 
 namespace uis {
 
@@ -88,6 +89,9 @@ struct BeamParams {
   float tc_sh, tc_sa;                  // power-of-two scales of the hidden columns and of a = relu(W1 h' + b1)
   float tc_inv_hh, tc_inv_1, tc_inv_2; // 1 / (weight scale * operand scale) per matrix
   float* tc_scratch;                   // [ctas][N][H]  a = relu(W1 h' + b1) between the W1 and the W2 product
+  // stationary-weights mode (uis_beam_stat.cuh)
+  unsigned* stat_bar;                  // [groups][32]: word 0 of a group = arrival counter of its barrier (zero at launch; one 128-byte line per group)
+  float* stat_scratch;                 // [groups][kCPCluster][H]  a = relu(W1 h' + b1), exchanged through L2
   // per-(CTA, lane) workspace
   float* pool_mean;    // [ctas*G][P][D]
   float* pool_hidden;  // [ctas*G][P][depth][H]
@@ -160,7 +164,7 @@ enum { LS_U = 0, LS_N, LS_TN, LS_T, LS_NB, LS_GEN, LS_ACTIVE, LS_FAILED, LS_TRAC
 // CTA scalars
 enum { MI_PUBLISHED = 0, MI_DONE, MI_MTOT, MI_QNEXT, MI_NLIST, MI_MAXK, MI_TCEXIT };
 
-template <int H, int D, int kCP = kCPBeam, bool XCL = false, int TCN = 0>
+template <int H, int D, int kCP = kCPBeam, bool XCL = false, int TCN = 0, bool STAT = false>
 __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
   SmemLayout L;
   unsigned o = 0;
@@ -170,7 +174,7 @@ __host__ __device__ inline SmemLayout make_layout(int B, int Kcap, int G) {
     L.xa = o;    o += TC::BOP_BYTES;
     L.xb = o;
   } else {
-    L.ring = o;  o += kStages * kStageBytes;
+    L.ring = o;  o += STAT ? align_up(StatCfg<H, D>::BYTES, 128) : kStages * kStageBytes;  // STAT: the resident weight rows
     L.xa = o;    o += H * kCP * 4;
     L.xb = o;    o += H * kCP * 4;
   }
@@ -673,6 +677,73 @@ __device__ __forceinline__ void run_pass_any(const BeamParams& p, const float* r
 #undef UIS_RP
 }
 
+// ---- stationary-weights pass (uis_beam_stat.cuh): columns [m0, m0 + Mp), Mp <= CP.  XA holds the source hidden states
+// [H][CP] (gathered by the caller); CTA `q` of the group computes its rows of the three products from the weights
+// resident in `sW` and publishes them through the group-shared slot pool / the L2 scratch; three group barriers.
+template <int H, int D, int CP, int NT>
+__device__ __forceinline__ void stat_pass(const BeamParams& p, const float* sW, float* XA, float* XB, const ColCtx cc, int m0,
+                                          int Mp, float* pool_mean_g, float* pool_hidden_g, float* scratch_g, unsigned* bar,
+                                          unsigned& epoch, int q, int tid, long long* ph, long long& tmark) {
+  using S = StatCfg<H, D>;
+  const size_t lane_pool_h = (size_t)p.P * H, lane_pool_m = (size_t)p.P * D;
+  // ---------------- GRU: rows g * UG + u  ->  h' of units q * UG + u
+  stat_dot<H, S::R0, CP, NT>(sW, S::LD, 0, XA, XB, Mp, tid);
+  named_bar_sync(1, NT);
+  if (tid < S::UG * CP) {
+    const int m = tid % CP, u = tid / CP, j = q * S::UG + u;
+    if (m < Mp) {
+      const float ar = stat_sum<S::R0, CP, NT>(XB, 0 * S::UG + u, m);
+      const float az = stat_sum<S::R0, CP, NT>(XB, 1 * S::UG + u, m);
+      const float an = stat_sum<S::R0, CP, NT>(XB, 2 * S::UG + u, m);
+      const float* gi = p.gi + (size_t)cc.girow[m0 + m] * 3 * H;
+      const float r = sigmoid_f32(__fadd_rn(gi[j], __fadd_rn(ar, __ldg(p.bhh + j))));
+      const float z = sigmoid_f32(__fadd_rn(gi[H + j], __fadd_rn(az, __ldg(p.bhh + H + j))));
+      const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(r, __fadd_rn(an, __ldg(p.bhh + 2 * H + j)))));
+      const float ho = XA[(size_t)j * CP + m];
+      pool_hidden_g[(size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H + j] =
+          __fadd_rn(__fmul_rn(__fsub_rn(ho, n), z), n);   // h' = (h - n) * z + n
+    }
+  }
+  stat_group_sync<NT>(bar, epoch, tid);
+  if (tid == 0) { const long long now_ = clock64(); ph[2] += now_ - tmark; tmark = now_; }
+  // ---------------- a = relu(W1 h' + b1): every CTA needs the whole h' columns (written by all CTAs of the group)
+  // (column by column so that a warp reads 128 contiguous bytes of one new slot; columns >= Mp of XA are still the
+  //  zeros the caller's gather of the source states put there)
+  for (int i = tid; i < Mp * H; i += NT) {
+    const int m = i / H, k = i % H;
+    XA[(size_t)k * CP + m] = __ldcg(pool_hidden_g + (size_t)cc.lane[m0 + m] * lane_pool_h + (size_t)cc.dst[m0 + m] * H + k);
+  }
+  named_bar_sync(1, NT);
+  stat_dot<H, S::R1, CP, NT>(sW, S::LD, S::R0, XA, XB, Mp, tid);
+  named_bar_sync(1, NT);
+  if (tid < S::R1 * CP) {
+    const int m = tid % CP, u = tid / CP, j = q * S::R1 + u;
+    if (m < Mp)
+      scratch_g[(size_t)m * H + j] = fmaxf(__fadd_rn(stat_sum<S::R1, CP, NT>(XB, u, m), __ldg(p.b1 + j)), 0.f);
+  }
+  stat_group_sync<NT>(bar, epoch, tid);
+  if (tid == 0) { const long long now_ = clock64(); ph[3] += now_ - tmark; tmark = now_; }
+  // ---------------- mean = W2 a + b2, then the running-mean update of the cluster (uisrnn.py:425-429)
+  for (int i = tid; i < Mp * H; i += NT) {
+    const int m = i / H, k = i % H;
+    XA[(size_t)k * CP + m] = __ldcg(scratch_g + (size_t)m * H + k);
+  }
+  named_bar_sync(1, NT);
+  stat_dot<H, S::R2, CP, NT>(sW, S::LD, S::R0 + S::R1, XA, XB, Mp, tid);
+  named_bar_sync(1, NT);
+  if (tid < S::R2 * CP) {
+    const int m = tid % CP, u = tid / CP, d = q * S::R2 + u;
+    if (m < Mp) {
+      const float mval = __fadd_rn(stat_sum<S::R2, CP, NT>(XB, u, m), __ldg(p.b2 + d));
+      const int n = cc.vis[m0 + m];  // visits BEFORE this one
+      const float mu_old = __ldcg(pool_mean_g + (size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.src[m0 + m] * D + d);
+      const float mu = (n == 0) ? mval : __fdiv_rn(__fadd_rn(__fmul_rn(mu_old, (float)(n - 1)), mval), (float)n);
+      pool_mean_g[(size_t)cc.lane[m0 + m] * lane_pool_m + (size_t)cc.dst[m0 + m] * D + d] = mu;
+    }
+  }
+  stat_group_sync<NT>(bar, epoch, tid);  // the next step scores against the new means / gathers the new hidden states
+}
+
 // ---- tensor-core weight pass (consumer warps' side; uis_beam_tc.cuh has the TMA producer and the MMA issuer) ----
 // Columns [m0, m0 + Mp), Mp <= N.  Thread <-> weight row: warp w reads TMEM lanes 32 * (w & 3) .. + 31 (the hardware
 // ties a warp to the lane quarter warp_id % 4) and takes the 8-column chunks of parity w >> 2.
@@ -819,19 +890,24 @@ __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* 
 // weight matrix by k-tiles, exchanging partial sums through distributed shared memory (xch_allreduce).
 // TCN > 0 = tensor-core pass (uis_beam_tc.cuh): the three matrix products of the step run as tcgen05 MMAs over
 // TCN columns per pass; warp NW drives the tensor-map TMA, warp NW + 1 issues the MMAs and owns the TMEM allocation.
-template <int H, int D, bool DEEP, bool XCL = false, int TCN = 0>
+// XM = 2: stationary-weights mode (uis_beam_stat.cuh): groups of 32 CTAs, one utterance stream per group, weights
+// resident in shared memory, products split by rows, group barriers in global memory (cooperative launch).
+template <int H, int D, bool DEEP, int XM = 0, int TCN = 0>
 __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __grid_constant__ BeamParams p) {
-  using C = Cfg<H, D, XCL ? kCPCluster : kCPBeam>;
+  constexpr bool XCL = XM == 1, STAT = XM == 2;
+  using C = Cfg<H, D, (XCL || STAT) ? kCPCluster : kCPBeam>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   constexpr bool TC = TCN > 0;
-  static_assert(!TC || (!DEEP && !XCL && NT == 256 && C::REBALANCE), "tensor-core pass: depth 1, one CTA per lane group");
+  static_assert(!TC || (!DEEP && !XCL && !STAT && NT == 256 && C::REBALANCE), "tensor-core pass: depth 1, one CTA per lane group");
+  static_assert(!STAT || (!DEEP && NT == 256), "stationary-weights mode: depth 1, 256 consumer threads");
   using TCC = TcCfg<TC ? H : 512, TC ? D : 256, TC ? TCN : 48>;  // (a valid placeholder for the FFMA kernels)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // the swizzled TMA boxes / MMA operands of the tensor-core pass need 1024-byte alignment
   unsigned char* smem = TC ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023)
                            : smem_raw;
   const int B = p.B, Kcap = p.Kcap, G = p.G;
-  const SmemLayout L = make_layout<H, D, C::CP, XCL, TCN>(B, Kcap, G);
+  const SmemLayout L = make_layout<H, D, C::CP, XCL, TCN, STAT>(B, Kcap, G);
+  const int sq = STAT ? (int)(blockIdx.x % kStatGroup) : 0, sgroup = STAT ? (int)(blockIdx.x / kStatGroup) : 0;
   float* ring = reinterpret_cast<float*>(smem + L.ring);
   float* XA = reinterpret_cast<float*>(smem + L.xa);
   float* XB = reinterpret_cast<float*>(smem + L.xb);
@@ -871,6 +947,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       mbar_init(&xbar[1], cluster_nctarank() - 1);
       misc[MI_QNEXT] = (int)cluster_id_x();  // utterances are dealt to the clusters round-robin (no atomic queue)
     }
+    if constexpr (STAT) misc[MI_QNEXT] = sgroup;  // ... and to the groups of the stationary-weights mode
     fence_mbar_init();
   }
   if constexpr (TC) {
@@ -899,6 +976,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
   };
 
   if (warp >= NW) {  // ---------------- producer warp (+ idle warps of its warpgroup)
+    if constexpr (STAT) return;  // nothing streams: the weights are resident
     if constexpr (TC) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // the unrolled MMA issue loop must not spill
     else if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if constexpr (TC) {
@@ -916,15 +994,16 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     return;
   }
   if constexpr (TC) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 8 x 32 x 232 + 4 x 32 x 40 <= 64 K registers
-  else if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  else if constexpr (C::REBALANCE && !STAT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
 
   // ---------------- consumer threads (tid < NT); they synchronise on named barrier 1
   auto lane_base = [&](int g) -> unsigned char* { return smem + L.lanes + (size_t)g * L.lane_stride; };
   auto LSp = [&](int g) -> volatile int* { return reinterpret_cast<volatile int*>(lane_base(g) + L.l_ls); };
   const int DH = p.depth * H;
   const size_t pool_m_stride = (size_t)p.P * D, pool_h_stride = (size_t)p.P * DH;
-  float* pool_mean_cta = p.pool_mean + (size_t)blockIdx.x * G * pool_m_stride;
-  float* pool_hidden_cta = p.pool_hidden + (size_t)blockIdx.x * G * pool_h_stride;
+  // (stationary-weights mode: the CTAs of a group share ONE slot pool -- every CTA writes its rows of the new slots)
+  float* pool_mean_cta = p.pool_mean + (size_t)(STAT ? sgroup : blockIdx.x) * G * pool_m_stride;
+  float* pool_hidden_cta = p.pool_hidden + (size_t)(STAT ? sgroup : blockIdx.x) * G * pool_h_stride;
   unsigned* bp_cta = p.bp + (size_t)blockIdx.x * G * p.maxN * B;
   const unsigned PW = (unsigned)(p.P + 31) / 32;
   const float INF = __int_as_float(0x7f800000);
@@ -939,6 +1018,8 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
   unsigned tc_tiles = 0;  // tensor-core pass: accumulator tiles consumed so far (identical in every consumer thread)
   float* tc_scratch_cta = TC ? p.tc_scratch + (size_t)blockIdx.x * (TC ? TCN : 1) * H : nullptr;
   if (tid < D) wv[tid] = p.wvec[tid];
+  unsigned stat_epoch = 0;
+  if constexpr (STAT) stat_load_weights<H, D, NT>(ring, p.whh_t, p.w1_t, p.w2_t, sq, tid);
   for (int g = 0; g < G; ++g) {
     if (tid < D) pool_mean_cta[g * pool_m_stride + (size_t)kInitSlot * D + tid] = p.mean0[tid];
     for (int q = tid; q < DH; q += NT) pool_hidden_cta[g * pool_h_stride + (size_t)kInitSlot * DH + q] = p.hidden0[q];
@@ -982,6 +1063,9 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
       if constexpr (XCL) {  // one lane per cluster; every CTA of the cluster draws the same sequence
         uidx = misc[MI_QNEXT];
         misc[MI_QNEXT] = uidx + (int)cluster_nclusters_x();
+      } else if constexpr (STAT) {
+        uidx = misc[MI_QNEXT];
+        misc[MI_QNEXT] = uidx + (int)(gridDim.x / kStatGroup);
       } else {
         uidx = atomicAdd(p.queue, 1);
       }
@@ -1068,7 +1152,9 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
             const float* mu = pool_mean_cta + cg[q] * pool_m_stride + (size_t)cslot[q] * D;
 #pragma unroll
             for (int i = 0; i < (D + 127) / 128; ++i)
-              if (lane * 4 + i * 128 < D) m4[q][i] = *reinterpret_cast<const float4*>(mu + lane * 4 + i * 128);
+              if (lane * 4 + i * 128 < D)
+                m4[q][i] = STAT ? __ldcg(reinterpret_cast<const float4*>(mu + lane * 4 + i * 128))  // written by other CTAs
+                                : *reinterpret_cast<const float4*>(mu + lane * 4 + i * 128);
           }
         }
         float acc[kBatch], d0sq[kBatch];
@@ -1504,7 +1590,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         UIS_PHASE(4);
       }
     } else {
-    if (Mtot == 0) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
+    if (Mtot == 0 && !STAT) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
     for (int m0 = 0; m0 < Mtot; m0 += C::CP) {
       const int Mp = min(C::CP, Mtot - m0);
       // gather the source hidden states, transposed: XA[k][m]
@@ -1517,16 +1603,18 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int m = 4 * c + q;
-            hv[q] = (m < Mp) ? pool_hidden_cta[(size_t)collane[m0 + m] * pool_h_stride +
-                                               (size_t)colsrc[m0 + m] * DH + j]
-                             : 0.f;
+            const float* hp = pool_hidden_cta + (size_t)collane[m0 + m] * pool_h_stride + (size_t)colsrc[m0 + m] * DH + j;
+            hv[q] = (m < Mp) ? (STAT ? __ldcg(hp) : *hp) : 0.f;
           }
           reinterpret_cast<float4*>(XA + (size_t)j * C::CP)[c] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
       }
       named_bar_sync(1, NT);
       UIS_PHASE(1);
-      if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
+      if constexpr (STAT)
+        stat_pass<H, D, C::CP, NT>(p, ring, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta,
+                                   p.stat_scratch + (size_t)sgroup * C::CP * H, p.stat_bar + (size_t)sgroup * kStatGroup, stat_epoch, sq, tid, ph, tmark);
+      else if (p.dbg_mode == 1) drain_pass<C>(full, empty, it, lane, p.depth, xsize);
       else run_pass_any<C, DEEP, XCL>(p, ring, full, empty, it, XA, XB, cc, m0, Mp, pool_mean_cta, pool_hidden_cta, bh, b1r, b2r, tid, lane, ph, tmark, &xc);
       named_bar_sync(1, NT);
       UIS_PHASE(4);
@@ -1571,7 +1659,9 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
         if (fin[g]) {  // utterance epilogue: back-track the best hypothesis (uisrnn.py:561)
           const int u = ls[LS_U], N = ls[LS_N];
           const long long row0 = ((long long)ls[LS_ROW0_HI] << 32) | (unsigned)ls[LS_ROW0_LO];
-          if (ls[LS_ERR] || ls[LS_NWIN] == 0) {
+          if (STAT && sq != 0) {
+            // (the replicas of a group decode the same utterance: CTA 0 of the group reports it)
+          } else if (ls[LS_ERR] || ls[LS_NWIN] == 0) {
             p.status[u] = ls[LS_ERR] ? -4 : -1;
             for (int i = 0; i < N; ++i) p.labels[row0 + i] = -1;
           } else {
@@ -1608,6 +1698,7 @@ __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __g
     __threadfence_block();
     misc[MI_DONE] = 1;
     if (XCL && xc.rank != 0) return;  // the replicas of a cluster count once
+    if (STAT && sq != 0) return;
     atomicAdd(&p.stats[0], (unsigned long long)st_cols);
     atomicAdd(&p.stats[1], (unsigned long long)st_pass);
     atomicAdd(&p.stats[2], (unsigned long long)st_cand);

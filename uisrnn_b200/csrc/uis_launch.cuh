@@ -12,6 +12,9 @@ bool launch_beam_small(int H, int D, const BeamParams& p, int ctas, unsigned sme
 bool launch_beam_cluster(int H, int D, const BeamParams& p, int ctas, int cluster, unsigned smem, cudaStream_t st,
                          cudaError_t* err);
 unsigned beam_cluster_smem(int H, int D, int B, int Kcap);
+// stationary-weights (latency) mode: `ctas` = groups * kStatGroup, cooperative launch; false if the shape has no instantiation
+bool launch_beam_stat(int H, int D, const BeamParams& p, int ctas, unsigned smem, cudaStream_t st, cudaError_t* err);
+unsigned beam_stat_smem(int H, int D, int B, int Kcap);
 // tensor-core pass (uis_beam_tc.cuh), N = columns per pass (32 or 48)
 bool beam_tc_supported(int H, int D, int N);
 unsigned beam_tc_smem(int H, int D, int N, int B, int Kcap, int G);
