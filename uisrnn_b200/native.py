@@ -271,14 +271,22 @@ class NativeModel:
     """seqs: list of C-contiguous float64 [N_u, D] arrays (host).  Returns a list of int32
     label arrays (and a dict of debug arrays when trace_utt is not None)."""
     n = len(seqs)
-    keep = [np.ascontiguousarray(s, dtype=np.float64) for s in seqs]
+    keep = [s if (type(s) is np.ndarray and s.dtype == np.float64 and s.flags.c_contiguous)
+            else np.ascontiguousarray(s, dtype=np.float64) for s in seqs]
     for s in keep:
       if s.ndim != 2 or s.shape[1] != self.D:
         raise ValueError('utterance shape {} does not match D={}'.format(s.shape, self.D))
-    lengths = (C.c_int64 * max(n, 1))(*[s.shape[0] for s in keep])
-    in_ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in keep])
-    outs = [np.empty(s.shape[0], np.int32) for s in keep]
-    out_ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+    # one flat int32 output buffer; the per-utterance pointers are base + 4 * offsets (no per-utterance allocation)
+    lens = np.fromiter((s.shape[0] for s in keep), dtype=np.int64, count=n) if n else np.zeros(1, np.int64)
+    offs = np.zeros(n + 1, np.int64)
+    np.cumsum(lens[:n], out=offs[1:])
+    flat = np.empty(max(int(offs[-1]), 1), np.int32)
+    outs = [flat[offs[i]:offs[i + 1]] for i in range(n)]
+    out_addr = (flat.ctypes.data + 4 * offs[:max(n, 1)]).astype(np.uint64)
+    in_addr = np.fromiter((s.ctypes.data for s in keep), dtype=np.uint64, count=n) if n else np.zeros(1, np.uint64)
+    lengths = lens.ctypes.data_as(C.POINTER(C.c_int64))
+    in_ptrs = in_addr.ctypes.data_as(C.POINTER(C.c_void_p))
+    out_ptrs = out_addr.ctypes.data_as(C.POINTER(C.c_void_p))
     opts = self._opts(beam_size, look_ahead, test_iteration, kcap, n_ctas, lanes, cluster, engine)
     taps, bufs, tp = None, None, None
     if trace_utt is not None:
