@@ -298,6 +298,7 @@ struct Plan {
   int B, L, T, Kcap, ctas, P, maxN, G;
   int cluster = 1;  // CTAs per utterance (thread-block cluster size); 1 = one CTA per lane group
   int stat = 0;     // > 0: stationary-weights mode with this many groups of 32 CTAs (uis_beam_stat.cuh)
+  bool stat_forced = false;
   int tcn = 0;      // > 0: tensor-core beam kernel with this many columns per pass (uis_beam_tc.cuh)
   bool cluster_forced = false;
   int node_cap = 0, leaf_cap = 0, maxTN = 0, maxSteps = 0;  // look_ahead >= 2 only
@@ -413,6 +414,7 @@ int make_plan(uis_model* m, const int64_t* off, int U, const uis_predict_opts* o
                      pl->B * kc + pl->B + 1 <= 65535;
     if (want && can) {
       pl->stat = std::max(1, std::min(ctas / uis::kStatGroup, U));
+      pl->stat_forced = o->cluster == uis::kStatGroup;
       pl->tcn = 0;
       pl->Kcap = kc;
       pl->P = pl->B * kc + pl->B + 1;
@@ -592,10 +594,18 @@ int run_device(uis_model* m, const float* x_dev, const int64_t* off, int U, cons
   if (pl.stat) {
     cudaError_t e = cudaSuccess;
     const bool have = uis::launch_beam_stat(H, D, p, pl.ctas, uis::beam_stat_smem(H, D, pl.B, pl.Kcap), st, &e);
-    if (!have) return fail(UIS_ERR_UNSUPPORTED, "no stationary-weights kernel for hidden=%d dim=%d", H, D);
-    if (e != cudaSuccess) return fail(UIS_ERR_CUDA, "stationary-weights beam kernel launch failed: %s", cudaGetErrorString(e));
-    cluster_used = uis::kStatGroup;
-    stat_done = true;
+    if (have && e == cudaSuccess) {
+      cluster_used = uis::kStatGroup;
+      stat_done = true;
+    } else if (pl.stat_forced) {
+      if (!have) return fail(UIS_ERR_UNSUPPORTED, "no stationary-weights kernel for hidden=%d dim=%d", H, D);
+      return fail(UIS_ERR_CUDA, "stationary-weights beam kernel launch failed: %s", cudaGetErrorString(e));
+    } else {
+      // chosen automatically and refused (e.g. the CTAs cannot all be co-resident on a shared / partitioned GPU): the
+      // one-CTA-per-utterance kernel runs on the same grid instead; its extra CTAs find the utterance queue empty
+      (void)cudaGetLastError();
+      cluster_used = 1;
+    }
   }
   if (stat_done) {
   } else if (pl.tcn) {
