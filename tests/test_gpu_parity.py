@@ -210,6 +210,24 @@ def _random_weights(H, D, seed, scale=1.0):
           'transition_bias': 0.2, 'crp_alpha': 0.7}
 
 
+def test_models_above_the_default_shape_run_in_the_1024x512_kernel(native):
+  """hidden up to 1024 / dim up to 512 (arguments.py:44-54 takes any int): the (1024, 512) instantiation of the fp32
+  FFMA engine, natively and zero-padded (hidden 600 / dim 300), against the oracle; above that the library refuses."""
+  rng = np.random.default_rng(11)
+  for H, D in ((1024, 512), (600, 300)):
+    w = _random_weights(H, D, seed=H + D)
+    model = native.NativeModel(w)
+    om = uis_oracle.OracleModel(w)
+    xs = [rng.standard_normal((n, D)) * 0.3 for n in (9, 4)]
+    got = model.predict(xs, beam_size=5, look_ahead=1, test_iteration=2, kcap=64)
+    assert model.stats()['engine'] == 1
+    for x, o in zip(xs, got):
+      assert o.tolist() == uis_oracle.predict_single(om, x, beam_size=5, look_ahead=1, test_iteration=2)
+  with pytest.raises(native.NativeError) as ei:
+    native.NativeModel(_random_weights(1100, 256, seed=1))
+  assert ei.value.code == native.UIS_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize('H,D', [(256, 128), (128, 64), (512, 256)])
 def test_random_models_all_kernel_shapes_match_oracle(native, H, D):
   """Every instantiated (hidden, dim) pair, untrained weights (cluster counts grow quickly here, so
@@ -301,7 +319,7 @@ def test_any_shape_up_to_512x256_runs_zero_padded(native, H, D, depth):
 
 
 def test_shapes_beyond_the_largest_kernel_fail_loudly(native):
-  H, D = 640, 256
+  H, D = 1152, 256
   z = lambda *s: np.zeros(s, np.float32)
   w = {'depth': 1, 'weight_ih_l0': z(3 * H, D), 'weight_hh_l0': z(3 * H, H), 'bias_ih_l0': z(3 * H), 'bias_hh_l0': z(3 * H),
        'w1': z(H, H), 'b1': z(H), 'w2': z(D, H), 'b2': z(D), 'h0': z(1, 1, H), 'sigma2': np.ones(D, np.float32),

@@ -127,6 +127,7 @@ unsigned smem_bytes(int H, int D, int B, int Kcap, int G) {
   if (H == 512 && D == 256) return uis::make_layout<512, 256>(B, Kcap, G).total;
   if (H == 256 && D == 128) return uis::make_layout<256, 128>(B, Kcap, G).total;
   if (H == 128 && D == 64) return uis::make_layout<128, 64>(B, Kcap, G).total;
+  if (H == 1024 && D == 512) return uis::make_layout<1024, 512, uis::beam_cp<1024>()>(B, Kcap, G).total;
   return 0xffffffffu;
 }
 
@@ -150,7 +151,7 @@ int dispatch_tree(int H, int D, const uis::BeamParams& p, int ctas, cudaStream_t
 }
 
 bool shape_supported(int H, int D) {
-  return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64);
+  return (H == 512 && D == 256) || (H == 256 && D == 128) || (H == 128 && D == 64) || (H == 1024 && D == 512);
 }
 
 // *cluster: in = planned cluster size, out = the one that was launched.  When the cluster size was chosen
@@ -709,15 +710,17 @@ int uis_model_create(uis_model** out, int device, int D, int H, int depth, const
   if (depth < 1 || depth > uis::kMaxDepth)
     return fail(UIS_ERR_UNSUPPORTED, "rnn_depth=%d: the sm_100a kernels support 1..%d stacked GRU layers", depth, uis::kMaxDepth);
   if (D < 1 || H < 1) return fail(UIS_ERR_INVALID, "observation_dim and rnn_hidden_size must be >= 1");
+  if ((H > 512 || D > 256) && depth > 1)
+    return fail(UIS_ERR_UNSUPPORTED, "hidden=%d dim=%d with rnn_depth=%d: models above hidden=512 / dim=256 run with one GRU layer", H, D, depth);
   if (shape_supported(H, D))
     return model_create_impl(out, device, D, H, depth, w_ih, w_hh, b_ih, b_hh, w1, b1, w2, b2, h0, sigma2,
                              transition_bias, crp_alpha, D, H);
-  static const int shapes[3][2] = {{128, 64}, {256, 128}, {512, 256}};
+  static const int shapes[4][2] = {{128, 64}, {256, 128}, {512, 256}, {1024, 512}};
   int Hp = 0, Dp = 0;
   for (auto& sh : shapes)
     if (!Hp && H <= sh[0] && D <= sh[1]) { Hp = sh[0]; Dp = sh[1]; }
   if (!Hp)
-    return fail(UIS_ERR_UNSUPPORTED, "hidden=%d dim=%d: the sm_100a kernels hold models up to hidden=512 dim=256", H, D);
+    return fail(UIS_ERR_UNSUPPORTED, "hidden=%d dim=%d: the sm_100a kernels hold models up to hidden=1024 dim=512", H, D);
   uis::DeviceGuard device_guard_(device);
   CU(device_guard_.status);
   std::vector<float> v, p_wih((size_t)3 * Hp * Dp + (size_t)(depth - 1) * 3 * Hp * Hp, 0.f), p_whh((size_t)depth * 3 * Hp * Hp, 0.f),

@@ -42,6 +42,9 @@ constexpr int kInitSlot = 0;            // pool slot holding (mean0, hidden0)
 #define UIS_CP_BEAM 20
 #endif
 constexpr int kCPBeam = UIS_CP_BEAM;             // GRU columns per weight pass, look_ahead-1 kernel (two lanes need <= 20 in ~99 % of the steps)
+// hidden sizes above 512: 8 columns per pass keep XA / XB (H x CP floats each) and the accumulator tile within budget
+template <int H> struct BeamCP { static constexpr int value = H > 512 ? 8 : kCPBeam; };
+template <int H> __host__ __device__ constexpr int beam_cp() { return BeamCP<H>::value; }
 constexpr int kCPCluster = 12;          // cluster (latency) mode: one lane per cluster, <= 12 columns per pass
 constexpr int kXchVals = 24;            // floats per thread and exchange round of the cluster K-split
 constexpr int kCPTree = 16;             // look-ahead tree kernel (shared memory goes to the node arrays instead)
@@ -895,7 +898,7 @@ __device__ __forceinline__ void tc_run_pass(const BeamParams& p, unsigned char* 
 template <int H, int D, bool DEEP, int XM = 0, int TCN = 0>
 __global__ void __launch_bounds__(Cfg<H, D>::BLOCK, 1) uis_beam_kernel(const __grid_constant__ BeamParams p) {
   constexpr bool XCL = XM == 1, STAT = XM == 2;
-  using C = Cfg<H, D, (XCL || STAT) ? kCPCluster : kCPBeam>;
+  using C = Cfg<H, D, (XCL || STAT) ? kCPCluster : BeamCP<H>::value>;
   constexpr int NT = C::NT, NW = C::NW, UPT = C::UPT;
   constexpr bool TC = TCN > 0;
   static_assert(!TC || (!DEEP && !XCL && !STAT && NT == 256 && C::REBALANCE), "tensor-core pass: depth 1, one CTA per lane group");

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) input_proj_kernel(const float* __restrict
 
 // One CTA of H threads.  Weights in the k-major layouts used by the beam kernel.
 // whh_t: [depth][H][3H]; wih_up_t: [depth-1][H][3H] (layers >= 1); bih: [depth][3H]; bhh: [depth][3H]; h0: [depth][H].
-__global__ void init_state_kernel(const float* __restrict__ whh_t, const float* __restrict__ wih_up_t,
+__global__ void __launch_bounds__(1024) init_state_kernel(const float* __restrict__ whh_t, const float* __restrict__ wih_up_t,
                                   const float* __restrict__ w1_t, const float* __restrict__ w2_t,
                                   const float* __restrict__ bih, const float* __restrict__ bhh,
                                   const float* __restrict__ b1, const float* __restrict__ b2,
