@@ -528,7 +528,9 @@ def run_b200(args):
   from uisrnn_b200.synth import synth_utt
   held, seqs = [], []
   for i in mine:
-    t = torch.from_numpy(synth_utt(FIRST_SEED + i, n_frames=N_FRAMES, dim=DIM)[0]).pin_memory()
+    t = torch.from_numpy(synth_utt(FIRST_SEED + i, n_frames=N_FRAMES, dim=DIM)[0])
+    if not args.pageable:
+      t = t.pin_memory()
     held.append(t)
     seqs.append(t.numpy())
   frames = U * N_FRAMES
@@ -694,11 +696,13 @@ def run_b200(args):
                   'uis_predict_wall': e2e_stats['host_ms'], 'h2d_copy_stream_span': e2e_stats['h2d_ms'],
                   'cast_and_input_projection_span_overlapped_with_h2d': e2e_stats['pipeline_ms'],
                   'beam_kernel': e2e_stats['beam_ms'], 'staging_chunks': e2e_stats['chunks'],
+                  'pinned_staging_by_host_threads': bool(e2e_stats.get('staged', 0)),
                   'python_and_gather': max(0.0, e2e_ms / args.steps - e2e_stats['host_ms'])},
               'path': ('uisrnn_b200.distributed.predict_sharded(UISRNN, list, lengths, root=0, as_arrays=True) -> shard_by_frames -> '
                        'uis_predict() per rank -> dist.gather of one int32 label tensor per rank -> int32 arrays on rank 0'
                        if world > 1 else
-                       'uisrnn.UISRNN.predict(list of pinned float64 ndarrays) -> uis_predict() C ABI: chunked H2D on a copy stream || '
+                       'uisrnn.UISRNN.predict(list of %s float64 ndarrays) -> uis_predict() C ABI: chunked H2D on a copy stream || ' % ('pageable' if args.pageable else 'pinned') +
+                       
                        'cast + input projection, beam kernel, one D2H copy of the int32 labels -> Python lists')},
       'gpu_launches': int(args.steps * 2),
       'clocks': clocks,
@@ -736,6 +740,7 @@ def main():
   ap.add_argument('--utts', type=int, default=888, help='utterances per GPU per step (6 lanes x 148 CTAs)')
   ap.add_argument('--engine', type=int, default=0, help='0 auto (tensor cores), 1 FFMA kernels, 2 tensor cores')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--pageable', action='store_true', help='e2e leg from ordinary (pageable) numpy arrays instead of pinned ones')
   ap.add_argument('--no-secondary', action='store_true', help='skip the config-3 / config-4 side measurements')
   args = ap.parse_args()
   if args.impl == 'reference':

@@ -111,7 +111,8 @@ typedef struct uis_stats {
   float host_ms;            /* wall time inside uis_predict()                                                          */
   int32_t chunks;           /* staging chunks the float64 rows travelled in                                            */
   int32_t groups;           /* > 1: the list did not fit the device at once and was decoded in this many groups        */
-  int32_t reserved_;
+  int32_t staged;           /* 1: the inputs were pageable and went through the library's pinned staging ring (host
+                               copy threads), 0: copied straight from the caller's (pinned) buffers                     */
 } uis_stats;
 
 int uis_version(void);

@@ -65,12 +65,25 @@ def test_lists_larger_than_the_row_budget_are_decoded_in_groups(toy_native, monk
     assert np.array_equal(a, b)
 
 
-def test_pageable_and_pinned_inputs_agree(toy_native):
+def test_pageable_and_pinned_inputs_agree(toy_native, monkeypatch):
+  """Pageable arrays (what numpy gives) travel through the library's pinned staging ring, filled by host threads;
+  pinned arrays are copied directly.  Forced both ways, small chunks so that the ring wraps."""
   import torch
-  xs, _ = toy_utterances()
-  xs = xs[:4]
+  xs, _ = _ragged()
+  monkeypatch.setenv('UISRNN_B200_CHUNK_MB', '0')
+  monkeypatch.setenv('UISRNN_B200_HOST_STAGING', '0')
   want = toy_native.predict(xs)
-  pinned = [torch.from_numpy(x).pin_memory().numpy() for x in xs]
+  assert toy_native.stats()['staged'] == 0
+  monkeypatch.setenv('UISRNN_B200_HOST_STAGING', '1')
+  for threads in ('1', '5'):
+    monkeypatch.setenv('UISRNN_B200_COPY_THREADS', threads)   # (the pool is created once per model: the first value counts)
+    got = toy_native.predict(xs)
+    st = toy_native.stats()
+    assert st['staged'] == 1 and st['chunks'] > 3
+    for a, b in zip(got, want):
+      assert np.array_equal(a, b)
+  monkeypatch.delenv('UISRNN_B200_HOST_STAGING')
+  pinned = [torch.from_numpy(x).pin_memory().numpy() if len(x) else x for x in xs]
   got = toy_native.predict(pinned)
   for a, b in zip(got, want):
     assert np.array_equal(a, b)

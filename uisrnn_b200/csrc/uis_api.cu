@@ -8,6 +8,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -84,6 +87,61 @@ struct DevBuf {
 
 }  // namespace
 
+namespace {
+// Host threads that copy the pieces of one staging chunk from the caller's PAGEABLE arrays into pinned memory, side by
+// side (a cudaMemcpy from pageable memory is staged by the driver in one thread at ~11 GB/s; several threads reach
+// the PCIe rate).  run() hands the same piece list to every worker; worker i copies bytes [total * i / n, total * (i + 1) / n).
+struct CopyPiece { const char* src; size_t dst_off, bytes; };
+class CopyPool {
+ public:
+  explicit CopyPool(int n) : n_(n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void run(const std::vector<CopyPiece>* pieces, char* dst, size_t total) {
+    { std::lock_guard<std::mutex> lk(mu_); pieces_ = pieces; dst_ = dst; total_ = total; pending_ = n_; ++gen_; }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+ private:
+  void loop(int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::vector<CopyPiece>* pieces; char* dst; size_t total;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        pieces = pieces_; dst = dst_; total = total_;
+      }
+      const size_t b0 = total * (size_t)i / (size_t)n_, b1 = total * (size_t)(i + 1) / (size_t)n_;
+      for (const CopyPiece& p : *pieces) {
+        const size_t lo = std::max(b0, p.dst_off), hi = std::min(b1, p.dst_off + p.bytes);
+        if (lo < hi) std::memcpy(dst + lo, p.src + (lo - p.dst_off), hi - lo);
+      }
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::vector<CopyPiece>* pieces_ = nullptr;
+  char* dst_ = nullptr;
+  size_t total_ = 0;
+  int pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+}  // namespace
+
 struct uis_model {
   int device = 0, D = 0, H = 0, depth = 1, num_sms = 0;  // D, H: the kernel shape the model runs in
   int D_user = 0, H_user = 0;  // the caller's shape (<= D, H): smaller models are zero-padded into the next kernel shape
@@ -119,6 +177,11 @@ struct uis_model {
   cudaEvent_t ev_pipe = nullptr;  // compute stream, before the first cast
   int32_t* labels_pin = nullptr;
   size_t labels_pin_cap = 0;
+  // pageable inputs: pinned staging ring (kSlots chunks) filled by host threads, one DMA per chunk
+  char* pin_stage = nullptr;
+  size_t pin_stage_cap = 0;
+  cudaEvent_t ev_dma[kSlots] = {nullptr, nullptr, nullptr};
+  CopyPool* copy_pool = nullptr;
 };
 
 namespace {
@@ -883,6 +946,10 @@ int uis_model_destroy(uis_model* m) {
   if (m->ev_pipe) cudaEventDestroy(m->ev_pipe);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->labels_pin) cudaFreeHost(m->labels_pin);
+  for (auto& e : m->ev_dma)
+    if (e) cudaEventDestroy(e);
+  if (m->pin_stage) cudaFreeHost(m->pin_stage);
+  delete m->copy_pool;
   delete m;
   return 0;
 }
@@ -998,20 +1065,76 @@ int predict_host_group_impl(uis_model* m, const double* const* seqs, const int64
     m->labels_pin_cap = want;
   }
   cudaStream_t cs = m->copy_stream;
+  // Pageable or pinned?  Ordinary numpy arrays are pageable: the driver would stage every cudaMemcpy itself, in one
+  // thread (measured 10.8 GB/s against 44.6 GB/s from pinned memory).  Such inputs go through a pinned ring of our own,
+  // filled by a few host threads while the previous chunk is on the bus.  UISRNN_B200_HOST_STAGING=0 / 1 overrides.
+  bool staged = false;
+  {
+    const char* env = std::getenv("UISRNN_B200_HOST_STAGING");
+    if (env && (env[0] == '0' || env[0] == '1')) {
+      staged = env[0] == '1';
+    } else if (rows * (size_t)D * 8 >= ((size_t)8 << 20)) {  // small inputs: not worth waking the threads
+      for (int q = 0; q < U && !staged; q += std::max(1, U / 8)) {  // a sample of the list
+        if (n_frames[q] <= 0) continue;
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, seqs[q]) != cudaSuccess) { (void)cudaGetLastError(); staged = true; }
+        else if (attr.type == cudaMemoryTypeUnregistered) staged = true;
+      }
+    }
+  }
+  const size_t chunk_bytes = chunk * (size_t)D * 8;
+  if (staged) {
+    if ((size_t)slots * chunk_bytes > m->pin_stage_cap) {
+      if (m->pin_stage) cudaFreeHost(m->pin_stage);
+      m->pin_stage = nullptr;
+      m->pin_stage_cap = 0;
+      if (cudaMallocHost(&m->pin_stage, (size_t)slots * chunk_bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        staged = false;  // no pinned memory to be had: let the driver stage the copies
+      } else {
+        m->pin_stage_cap = (size_t)slots * chunk_bytes;
+      }
+    }
+    for (auto& e : m->ev_dma)
+      if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (staged && !m->copy_pool) {
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      int nthreads = (int)std::min(16u, std::max(2u, hw / 2));  // measured on the B200 box: 4 -> 40 ms, 8 -> 29 ms, 16 -> 23 ms for 909 MB
+      if (const char* env = std::getenv("UISRNN_B200_COPY_THREADS")) nthreads = std::max(1, std::min(64, std::atoi(env)));
+      m->copy_pool = new CopyPool(nthreads);
+    }
+  }
   CU(cudaEventRecord(m->ev_h2d[0], cs));
   CU(cudaEventRecord(m->ev_pipe, st));
   size_t r0 = 0;
   int u = 0;
+  std::vector<CopyPiece> pieces;
   for (int c = 0; r0 < rows; ++c) {
     const size_t r1 = std::min(rows, r0 + chunk);
     const int slot = c % uis_model::kSlots;
     double* stage = m->x64.as<double>() + (size_t)slot * chunk * D;
-    if (c >= uis_model::kSlots) CU(cudaStreamWaitEvent(cs, m->ev_free[slot], 0));  // cast of chunk c - kSlots has read the slot
-    for (size_t r = r0; r < r1;) {
-      while (u < U && (size_t)off[u + 1] <= r) ++u;  // the utterance that holds row r (empty ones are skipped)
-      const size_t take = std::min((size_t)off[u + 1], r1) - r;
-      CU(cudaMemcpyAsync(stage + (r - r0) * D, seqs[u] + (r - (size_t)off[u]) * D, take * D * 8, cudaMemcpyHostToDevice, cs));
-      r += take;
+    if (staged) {
+      pieces.clear();
+      for (size_t r = r0; r < r1;) {
+        while (u < U && (size_t)off[u + 1] <= r) ++u;
+        const size_t take = std::min((size_t)off[u + 1], r1) - r;
+        pieces.push_back(CopyPiece{reinterpret_cast<const char*>(seqs[u] + (r - (size_t)off[u]) * D), (r - r0) * D * 8, take * D * 8});
+        r += take;
+      }
+      char* pin = m->pin_stage + (size_t)slot * chunk_bytes;
+      if (c >= uis_model::kSlots) CU(cudaEventSynchronize(m->ev_dma[slot]));  // the DMA out of this pinned slot is done
+      m->copy_pool->run(&pieces, pin, (r1 - r0) * D * 8);
+      if (c >= uis_model::kSlots) CU(cudaStreamWaitEvent(cs, m->ev_free[slot], 0));
+      CU(cudaMemcpyAsync(stage, pin, (r1 - r0) * D * 8, cudaMemcpyHostToDevice, cs));
+      CU(cudaEventRecord(m->ev_dma[slot], cs));
+    } else {
+      if (c >= uis_model::kSlots) CU(cudaStreamWaitEvent(cs, m->ev_free[slot], 0));  // cast of chunk c - kSlots has read the slot
+      for (size_t r = r0; r < r1;) {
+        while (u < U && (size_t)off[u + 1] <= r) ++u;  // the utterance that holds row r (empty ones are skipped)
+        const size_t take = std::min((size_t)off[u + 1], r1) - r;
+        CU(cudaMemcpyAsync(stage + (r - r0) * D, seqs[u] + (r - (size_t)off[u]) * D, take * D * 8, cudaMemcpyHostToDevice, cs));
+        r += take;
+      }
     }
     CU(cudaEventRecord(m->ev_copied[slot], cs));
     CU(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
@@ -1031,6 +1154,7 @@ int predict_host_group_impl(uis_model* m, const double* const* seqs, const int64
   if (int rc = run_device(m, m->x32.as<float>(), off, U, pl, m->labels.as<int32_t>(), taps, st, /*gi_ready=*/true)) return rc;
   m->stats.kernel_launches = 1 + 2 * (int64_t)n_chunks;
   m->stats.chunks = n_chunks;
+  m->stats.staged = staged ? 1 : 0;
   CU(cudaMemcpyAsync(m->labels_pin, m->labels.p, rows * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   for (int q = 0; q < U; ++q)
@@ -1050,7 +1174,7 @@ void add_stats(uis_stats* a, const uis_stats& b) {
   a->engine = std::max(a->engine, b.engine); a->tc_columns = std::max(a->tc_columns, b.tc_columns);
   for (int i = 0; i < 10; ++i) a->phase_cycles[i] += b.phase_cycles[i];
   for (int i = 0; i < 4; ++i) a->tc_cycles[i] += b.tc_cycles[i];
-  a->chunks += b.chunks; a->groups += b.groups;
+  a->chunks += b.chunks; a->groups += b.groups; a->staged = std::max(a->staged, b.staged);
 }
 
 }  // namespace

@@ -50,7 +50,7 @@ class Stats(C.Structure):
               ('prepass_ms', C.c_float), ('beam_ms', C.c_float), ('lanes', C.c_int32), ('cluster', C.c_int32), ('engine', C.c_int32),
               ('tc_columns', C.c_int32), ('phase_cycles', C.c_int64 * 10), ('tc_cycles', C.c_int64 * 4),
               ('h2d_ms', C.c_float), ('pipeline_ms', C.c_float), ('host_ms', C.c_float), ('chunks', C.c_int32),
-              ('groups', C.c_int32), ('reserved_', C.c_int32)]
+              ('groups', C.c_int32), ('staged', C.c_int32)]
 
   def as_dict(self):
     out = {}
