@@ -366,18 +366,23 @@ class UISRNN:
   # ------------------------------------------------------------------ inference
   def _fingerprint(self):
     """Identity of the parameter values the device-side twin was built from.  `_version` does not move on
-    edits through `.data` (an idiom the reference's own tests use), so a cheap content checksum -- sum and
-    sum of squares per tensor, one fused reduction -- is part of the key."""
+    edits through `.data` (an idiom the reference's own tests use), so a cheap content checksum -- the L2 and L1
+    norms of every tensor, two fused multi-tensor reductions -- is part of the key."""
     tensors = list(self.rnn_model.parameters()) + [self.rnn_init_hidden, self.sigma2]
     with torch.no_grad():
       by_device = {}  # the parameters need not share a device (callers assign rnn_init_hidden / sigma2 freely)
       for i, t in enumerate(tensors):
-        d = t.detach().double()
-        by_device.setdefault(t.device, []).append((i, torch.stack((d.sum(), (d * d).sum()))))
+        by_device.setdefault(t.device, []).append((i, t.detach()))
       sums = [None] * len(tensors)
-      for parts in by_device.values():  # one reduction batch and one device -> host copy per device
-        flat = torch.stack([s for _, s in parts]).cpu().tolist()
-        for (i, _), pair in zip(parts, flat):
+      for parts in by_device.values():  # two fused multi-tensor reductions and one device -> host copy per device
+        ts = [t for _, t in parts]
+        try:
+          n2, n1 = torch._foreach_norm(ts, 2), torch._foreach_norm(ts, 1)  # pylint: disable=protected-access
+          flat = torch.stack(list(n2) + list(n1)).double().cpu().tolist()
+          pairs = list(zip(flat[:len(ts)], flat[len(ts):]))
+        except (AttributeError, RuntimeError, TypeError):  # no multi-tensor kernels in this torch: one by one
+          pairs = [tuple(torch.stack((t.double().norm(2), t.double().norm(1))).cpu().tolist()) for t in ts]
+        for (i, _), pair in zip(parts, pairs):
           sums[i] = tuple(pair)
     return (tuple((t.data_ptr(), t._version) for t in tensors), tuple(sums),
             self.transition_bias, self.crp_alpha)
