@@ -207,3 +207,27 @@ def test_resize_indices_and_batch_sampler_mirror_the_data_path():
     for column, k in enumerate(chosen):
       assert np.array_equal(x[1:lengths[column], column, :], subs[k])
       assert not x[0, column].any() and not x[lengths[column]:, column].any()
+
+
+def test_param_order_and_dropout_mask_contract():
+  """Host side of the device trainer's contracts: the tensor order uis_trainer_create takes for stacked layers, and
+  the dropout keep mask (a pure function of seed, iteration, layer, element) restated in numpy."""
+  from uisrnn_b200 import native
+  assert native.param_order(1) == native.PARAM_ORDER and len(native.PARAM_ORDER) == 10
+  order = native.param_order(3)
+  assert len(order) == 4 * 3 + 6
+  assert order[:4] == ('gru.weight_ih_l0', 'gru.weight_hh_l0', 'gru.bias_ih_l0', 'gru.bias_hh_l0')
+  assert order[8:12] == ('gru.weight_ih_l2', 'gru.weight_hh_l2', 'gru.bias_ih_l2', 'gru.bias_hh_l2')
+  assert order[-6:] == ('linear_mean1.weight', 'linear_mean1.bias', 'linear_mean2.weight', 'linear_mean2.bias',
+                        'rnn_init_hidden', 'sigma2')
+  a = native.dropout_keep_mask(0x1234567890, 3, 1, 200000, 0.2)
+  b = native.dropout_keep_mask(0x1234567890, 3, 1, 200000, 0.2)
+  assert a.dtype == bool and np.array_equal(a, b)                       # reproducible
+  assert abs(a.mean() - 0.8) < 0.01                                     # keeps 1 - p of the elements
+  for other in (native.dropout_keep_mask(0x1234567890, 4, 1, 200000, 0.2),    # another iteration,
+                native.dropout_keep_mask(0x1234567890, 3, 0, 200000, 0.2),    # another layer,
+                native.dropout_keep_mask(0x1234567891, 3, 1, 200000, 0.2)):   # another seed: another mask
+    assert 0.3 < (a != other).mean() < 0.34                             # two independent masks differ in 2 p (1 - p)
+  assert native.dropout_keep_mask(7, 0, 0, 1000, 0.0).all()
+  # a prefix of a longer mask is the shorter mask (element i depends on i only)
+  assert np.array_equal(native.dropout_keep_mask(5, 1, 0, 100, 0.5), native.dropout_keep_mask(5, 1, 0, 1000, 0.5)[:100])
